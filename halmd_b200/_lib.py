@@ -1,0 +1,126 @@
+"""ctypes binding of the C ABI declared in include/halmd_b200.h (kernel level) and
+include/halmd_b200_modules.h (module level).
+
+The shared library is built in-tree by ``halmd_b200/csrc/Makefile`` (``__graft_entry__.build()``).
+There is no CPU fallback: if the library is missing the import fails loudly, and every compute
+entry point returns an error code that is raised as :class:`HxError`.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhalmd_b200.so")
+
+PLACEHOLDER = 0xFFFFFFFF
+LAYOUT_COLUMN, LAYOUT_ROW = 0, 1
+TRUNC_SHARP, TRUNC_SHIFTED, TRUNC_SMOOTH_R4 = 0, 1, 2
+MAX_PAIR_TYPES = 16
+
+
+class HxError(RuntimeError):
+    pass
+
+
+class LjParams(C.Structure):
+    _fields_ = [
+        ("ntype1", C.c_uint), ("ntype2", C.c_uint), ("truncation", C.c_int), ("rri_smooth", C.c_float),
+        ("epsilon", C.c_float * MAX_PAIR_TYPES), ("sigma2", C.c_float * MAX_PAIR_TYPES),
+        ("r_cut", C.c_float * MAX_PAIR_TYPES), ("rr_cut", C.c_float * MAX_PAIR_TYPES),
+        ("en_cut", C.c_float * MAX_PAIR_TYPES),
+    ]
+
+
+class Rand48(C.Structure):
+    _fields_ = [("blocks", C.c_uint), ("threads", C.c_uint), ("a", C.c_uint16 * 3), ("c", C.c_uint16 * 3)]
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build the CUDA extension first "
+        "(python -c 'import __graft_entry__ as g; g.build()' or make -C halmd_b200/csrc). "
+        "halmd_b200 has no CPU fallback."
+    )
+
+lib = C.CDLL(LIB_PATH)
+
+P = C.c_void_p
+F3 = C.POINTER(C.c_float)
+D3 = C.POINTER(C.c_double)
+U3 = C.POINTER(C.c_uint)
+SZ = C.c_size_t
+
+_protos = {
+    "hx_version": (C.c_int, []),
+    "hx_last_error_string": (C.c_char_p, []),
+    "hx_device_count": (C.c_int, []),
+    "hx_launch_count": (C.c_uint64, []),
+    "hx_array_size": (SZ, [SZ]),
+    "hx_state_init": (C.c_int, [P, P, P, P, P, P, SZ, SZ, P]),
+    "hx_binning_plan": (C.c_int, [D3, SZ, C.c_float, C.c_float, C.c_double, U3, F3, U3]),
+    "hx_binning_update": (C.c_int, [P, SZ, F3, U3, C.c_uint, P, P, P, P, P]),
+    "hx_hilbert_depth": (C.c_uint, [D3]),
+    "hx_hilbert_keys": (C.c_int, [P, SZ, F3, C.c_uint, P, P]),
+    "hx_iota_u32": (C.c_int, [P, SZ, P]),
+    "hx_sort_scratch_bytes": (SZ, [SZ]),
+    "hx_sort_pairs_stable_u32": (C.c_int, [P, P, SZ, C.c_uint, P, SZ, P]),
+    "hx_state_permute": (C.c_int, [P, SZ, SZ, P, P, P, P, P, P, P, P, P, P]),
+    "hx_displacement_zero": (C.c_int, [P, P, SZ, P]),
+    "hx_displacement_max": (C.c_int, [P, P, SZ, F3, P, C.c_int, P]),
+    "hx_displacement_exceeds": (C.c_int, [C.c_uint32, C.c_double]),
+    "hx_nlist_plan": (C.c_int, [C.c_float, C.c_float, SZ, C.c_double, C.c_double, C.c_uint, U3]),
+    "hx_nlist_build": (C.c_int, [P, U3, C.c_uint, P, SZ, F3, C.c_uint, C.c_uint, F3, P, C.c_uint, SZ,
+                                 C.c_int, C.c_int, P, P, P]),
+    "hx_potential_lj_init": (C.c_int, [C.POINTER(LjParams), C.c_uint, C.c_uint, F3, F3, C.c_int, F3, C.c_float]),
+    "hx_pair_force": (C.c_int, [C.POINTER(LjParams), P, P, P, C.c_uint, SZ, C.c_int, SZ, F3, C.c_int,
+                                C.c_float, P, P, P, SZ, P]),
+    "hx_pair_force_guarded": (C.c_int, [C.POINTER(LjParams), P, P, P, C.c_uint, SZ, C.c_int, SZ, F3, C.c_int,
+                                        C.c_float, P, P, P, SZ, P, C.c_float, P]),
+    "hx_pair_force_set_lanes": (C.c_int, [C.c_int]),
+    "hx_verlet_integrate": (C.c_int, [P, P, P, P, SZ, C.c_float, F3, P]),
+    "hx_verlet_finalize": (C.c_int, [P, P, SZ, C.c_float, P]),
+    "hx_verlet_finalize_integrate": (C.c_int, [P, P, P, P, SZ, SZ, C.c_float, F3, C.c_int, P, P, P]),
+    "hx_verlet_finalize_guarded": (C.c_int, [P, P, SZ, C.c_float, P, P]),
+    "hx_rand48_seed": (C.c_int, [C.POINTER(Rand48), C.c_uint, C.c_uint, C.c_uint, P, P]),
+    "hx_rand48_uniform": (C.c_int, [C.POINTER(Rand48), P, P, SZ, P]),
+    "hx_andersen_finalize": (C.c_int, [P, P, SZ, SZ, C.c_float, C.c_float, C.c_float, C.POINTER(Rand48), P, P]),
+    "hx_andersen_finalize_guarded": (C.c_int, [P, P, SZ, SZ, C.c_float, C.c_float, C.c_float,
+                                               C.POINTER(Rand48), P, P, P]),
+    "hx_sample_positions": (C.c_int, [P, P, P, SZ, F3, P, P]),
+    "hx_sample_velocities": (C.c_int, [P, P, SZ, P, P]),
+    "hx_msd_scratch_bytes": (SZ, [C.c_uint]),
+    "hx_msd_block": (C.c_int, [P, P, C.c_uint, SZ, P, P, SZ, P]),
+    "hx_density_modes": (C.c_int, [P, SZ, P, C.c_uint, P, P]),
+    "hx_thermodynamics": (C.c_int, [P, P, P, SZ, SZ, P, P]),
+    "hx_ctl_reset": (C.c_int, [P, P]),
+}
+
+KERNEL_SYMBOLS = tuple(_protos)
+
+for _name, (_res, _args) in _protos.items():
+    _fn = getattr(lib, _name)   # AttributeError here = header/library mismatch: fail loudly
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(rc, what=""):
+    """Raise HxError for a non-zero return code of an hx_* call."""
+    if rc != 0:
+        msg = lib.hx_last_error_string().decode(errors="replace")
+        raise HxError(f"{what or 'hx call'} failed (code {rc}): {msg}")
+
+
+def f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+def d3(v):
+    return (C.c_double * 3)(*[float(x) for x in v])
+
+
+def u3(v):
+    return (C.c_uint * 3)(*[int(x) for x in v])
+
+
+def farr(v):
+    v = [float(x) for x in v]
+    return (C.c_float * len(v))(*v)

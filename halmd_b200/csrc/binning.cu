@@ -1,0 +1,124 @@
+// Cell binning: particle → cell index → fixed-size cell placeholders.
+//
+// Reference: halmd/mdsim/gpu/binning.cpp:166-221 runs compute_cell + a 4-pass radix sort of all
+// particles + find_cell_offset + assign_cells (binning_kernel.cu:34-139).  The observable result is
+// g_cell[c*cell_size + s] = s-th smallest particle index in cell c, padded with placeholders, and an
+// overflow flag when a cell has >= cell_size particles.  Here the same array is produced without a
+// global sort: atomic slot claiming per cell (order-free) followed by a warp-local bitonic sort of
+// each cell's few entries, which restores the ascending-index order of the stable sort.
+#include "common.cuh"
+
+namespace hx {
+
+// cell index of a position, binning_kernel.cu:34-54:  (uint)(r / l + n) % n, x fastest.
+// IEEE division (the reference's -prec-div=false division differs by <= 2 ulp).
+__device__ __forceinline__ unsigned cell_coord(float r, float len, unsigned n)
+{
+    float t = __fadd_rn(__fdiv_rn(r, len), static_cast<float>(n));
+    return __float2uint_rz(t) % n;
+}
+
+__global__ void k_cell_claim(const float4* __restrict__ pos_hi, unsigned n, vec3 cell_len, uvec3 ncell,
+                             unsigned cell_size, unsigned* __restrict__ cell_count,
+                             unsigned* __restrict__ g_cell, unsigned* __restrict__ cell_index)
+{
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pos_hi[i];
+    if (__float_as_uint(p.w) == HX_PH) {
+        if (cell_index) cell_index[i] = HX_PH;
+        return;
+    }
+    unsigned cx = cell_coord(p.x, cell_len.x, ncell.x);
+    unsigned cy = cell_coord(p.y, cell_len.y, ncell.y);
+    unsigned cz = cell_coord(p.z, cell_len.z, ncell.z);
+    unsigned c = (cz * ncell.y + cy) * ncell.x + cx;
+    if (cell_index) cell_index[i] = c;
+    unsigned s = atomicAdd(&cell_count[c], 1u);
+    if (s < cell_size) g_cell[static_cast<size_t>(c) * cell_size + s] = i;
+}
+
+// one warp per cell: sort the claimed entries ascending (placeholders = 0xFFFFFFFF sort last)
+__global__ void k_cell_sort(unsigned* __restrict__ g_cell, const unsigned* __restrict__ cell_count,
+                            unsigned ncells, unsigned cell_size, unsigned pow2, int* __restrict__ overflow)
+{
+    extern __shared__ unsigned s_all[];
+    unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    unsigned c = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (c >= ncells) return;
+    unsigned cnt = cell_count[c];
+    if (cnt >= cell_size) {
+        // binning_kernel.cu:124-127 — last placeholder occupied ⇒ overcrowded
+        if (lane == 0) *overflow = 1;
+        cnt = cell_size;
+    }
+    if (cnt < 2) return;
+    // smallest power of two >= cnt, bounded by pow2 (>= cell_size)
+    unsigned m = 2;
+    while (m < cnt) m <<= 1;
+    unsigned* s = s_all + warp * pow2;
+    unsigned* cell = g_cell + static_cast<size_t>(c) * cell_size;
+    for (unsigned k = lane; k < m; k += 32) s[k] = (k < cnt) ? cell[k] : HX_PH;
+    __syncwarp();
+    for (unsigned size = 2; size <= m; size <<= 1) {
+        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+            for (unsigned t = lane; t < (m >> 1); t += 32) {
+                unsigned lo = 2 * t - (t & (stride - 1));   // index with the `stride` bit clear
+                unsigned hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                unsigned a = s[lo], b = s[hi];
+                if ((a > b) == up) { s[lo] = b; s[hi] = a; }
+            }
+            __syncwarp();
+        }
+    }
+    for (unsigned k = lane; k < cnt; k += 32) cell[k] = s[k];
+}
+
+} // namespace hx
+
+using namespace hx;
+
+extern "C" int hx_binning_update(const hx_float4* position_hi_dev, size_t nparticle,
+                                 const float cell_length[3], const unsigned ncell[3], unsigned cell_size,
+                                 uint32_t* g_cell_dev, uint32_t* cell_count_dev, uint32_t* cell_index_dev,
+                                 int* overflow_flag_dev, void* stream)
+{
+    if (!position_hi_dev || !cell_length || !ncell || !g_cell_dev || !cell_count_dev || !overflow_flag_dev
+        || cell_size == 0 || cell_size % 32 != 0) {
+        set_error("hx_binning_update: invalid argument (cell size must be a multiple of warp size 32)");
+        return HX_E_INVALID;
+    }
+    size_t ncells = static_cast<size_t>(ncell[0]) * ncell[1] * ncell[2];
+    if (ncells == 0 || ncells * cell_size >= 0xFFFFFFFFull || nparticle >= 0xFFFFFFFFull) {
+        set_error("hx_binning_update: cell grid out of range");
+        return HX_E_INVALID;
+    }
+    cudaStream_t st = as_stream(stream);
+    cudaError_t err;
+    if ((err = cudaMemsetAsync(cell_count_dev, 0, ncells * sizeof(uint32_t), st)) != cudaSuccess
+        || (err = cudaMemsetAsync(g_cell_dev, 0xFF, ncells * cell_size * sizeof(uint32_t), st)) != cudaSuccess) {
+        set_error("hx_binning_update: memset: %s", cudaGetErrorString(err));
+        return static_cast<int>(err);
+    }
+    vec3 cl = make_vec3(cell_length);
+    uvec3 nc = {ncell[0], ncell[1], ncell[2]};
+    if (nparticle > 0) {
+        k_cell_claim<<<div_up(nparticle, 256), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(position_hi_dev), static_cast<unsigned>(nparticle), cl, nc,
+            cell_size, cell_count_dev, g_cell_dev, cell_index_dev);
+        int rc = check_launch("k_cell_claim");
+        if (rc) return rc;
+    }
+    unsigned pow2 = 32;
+    while (pow2 < cell_size) pow2 <<= 1;
+    unsigned warps = 4;
+    while (warps > 1 && warps * pow2 * sizeof(unsigned) > 48 * 1024) warps >>= 1;
+    if (warps * pow2 * sizeof(unsigned) > 48 * 1024) {
+        set_error("hx_binning_update: cell size %u too large", cell_size);
+        return HX_E_UNSUPPORTED;
+    }
+    k_cell_sort<<<div_up(ncells, warps), warps * 32, warps * pow2 * sizeof(unsigned), st>>>(
+        g_cell_dev, cell_count_dev, static_cast<unsigned>(ncells), cell_size, pow2, overflow_flag_dev);
+    return check_launch("k_cell_sort");
+}

@@ -1,0 +1,166 @@
+// Library plumbing + host-side sizing formulas of the reference modules.
+#include "common.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+
+namespace hx {
+
+std::atomic<uint64_t> g_launches{0};
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what)
+{
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(err));
+        return static_cast<int>(err);
+    }
+    return HX_OK;
+}
+
+} // namespace hx
+
+using namespace hx;
+
+extern "C" {
+
+int hx_version(void) { return 100; }
+
+const char* hx_last_error_string(void) { return g_error; }
+
+int hx_device_count(void)
+{
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess || n == 0) {
+        set_error("no CUDA device: %s", cudaGetErrorString(err));
+        return HX_E_NOGPU;
+    }
+    return n;
+}
+
+uint64_t hx_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// halmd/mdsim/gpu/particle.cpp:69-88 — round up to a multiple of max threads per block (1024)
+size_t hx_array_size(size_t nparticle)
+{
+    size_t const block = 1024;
+    size_t a = nparticle > 0 ? (nparticle + block - 1) / block : 1;
+    return a * block;
+}
+
+// halmd/mdsim/gpu/binning.cpp:81-116 — cell grid and placeholders per cell
+int hx_binning_plan(const double box_length[3], size_t nparticle, float r_cut_max, float skin,
+                    double occupancy, unsigned ncell[3], float cell_length[3], unsigned* cell_size)
+{
+    if (!box_length || !ncell || !cell_length || !cell_size || occupancy <= 0 || nparticle == 0) {
+        set_error("hx_binning_plan: invalid argument");
+        return HX_E_INVALID;
+    }
+    double const warp_size = 32;
+    double nwarps = nparticle / (occupancy * warp_size);
+    double volume = 1.;
+    for (int d = 0; d < 3; ++d) volume *= box_length[d];
+    size_t ncells = 1;
+    for (int d = 0; d < 3; ++d) {
+        // upper bound: cell_length > r_c + r_skin (float arithmetic as in the reference members)
+        unsigned ncell_max = static_cast<unsigned>(box_length[d] / static_cast<double>(r_cut_max + skin));
+        // fixed_vector<double> = float length * pow(...)
+        unsigned want = static_cast<unsigned>(std::ceil(box_length[d] * std::pow(nwarps / volume, 1. / 3)));
+        ncell[d] = std::min(want, ncell_max);
+        if (ncell[d] == 0) {
+            set_error("hx_binning_plan: box too small for cutoff");
+            return HX_E_INVALID;
+        }
+        cell_length[d] = static_cast<float>(box_length[d]) / static_cast<float>(ncell[d]);
+        ncells *= ncell[d];
+    }
+    *cell_size = static_cast<unsigned>(warp_size * static_cast<size_t>(std::ceil(nwarps / ncells)));
+    return HX_OK;
+}
+
+// halmd/mdsim/gpu/neighbours/from_binning.cpp:96-119 — placeholders per neighbour list
+int hx_nlist_plan(float r_cut_max, float skin, size_t nparticle2, double box_volume,
+                  double occupancy, unsigned cell_size, unsigned* size)
+{
+    if (!size || occupancy <= 0 || box_volume <= 0) {
+        set_error("hx_nlist_plan: invalid argument");
+        return HX_E_INVALID;
+    }
+    float const unit_sphere3 = static_cast<float>(4 * M_PI / 3);
+    float neighbour_sphere = static_cast<float>(unit_sphere3 * std::pow(r_cut_max + skin, 3));
+    float density = static_cast<float>(nparticle2 / box_volume);
+    size_t s = static_cast<size_t>(std::ceil(neighbour_sphere * (density / occupancy)));
+    *size = static_cast<unsigned>(std::max<size_t>(s, cell_size));
+    return HX_OK;
+}
+
+// halmd/mdsim/gpu/sorts/hilbert.cpp:51-54
+unsigned hx_hilbert_depth(const double box_length[3])
+{
+    float max_length = static_cast<float>(std::max(box_length[0], std::max(box_length[1], box_length[2])));
+    unsigned depth = static_cast<unsigned>(std::ceil(std::log(max_length) / M_LN2));
+    return std::min(10u, depth);
+}
+
+// from_binning.cpp:130-131 — float(displacement) > float(skin / 2), displacement = sqrt(float)
+int hx_displacement_exceeds(uint32_t max_rr_bits, double skin)
+{
+    float rr;
+    std::memcpy(&rr, &max_rr_bits, 4);
+    float d = std::sqrt(rr);
+    return d > static_cast<float>(static_cast<float>(skin) / 2) ? 1 : 0;
+}
+
+// lennard_jones.cpp:44-70, smooth_r4.hpp:55-91 (float matrices, float formulas)
+int hx_potential_lj_init(hx_lj_params* p, unsigned ntype1, unsigned ntype2, const float* epsilon,
+                         const float* sigma, int truncation, const float* cutoff_sigma, float h)
+{
+    if (!p || !epsilon || !sigma || !cutoff_sigma || ntype1 == 0 || ntype2 == 0
+        || ntype1 * ntype2 > HX_MAX_PAIR_TYPES) {
+        set_error("hx_potential_lj_init: invalid argument (ntype1*ntype2 must be in 1..%d)", HX_MAX_PAIR_TYPES);
+        return HX_E_INVALID;
+    }
+    if (truncation < HX_TRUNC_SHARP || truncation > HX_TRUNC_SMOOTH_R4) {
+        set_error("hx_potential_lj_init: unknown truncation %d", truncation);
+        return HX_E_UNSUPPORTED;
+    }
+    std::memset(p, 0, sizeof(*p));
+    p->ntype1 = ntype1;
+    p->ntype2 = ntype2;
+    p->truncation = truncation;
+    // rri_smooth_(std::pow(h, -2)): pow(float, int) is evaluated in double, stored as float
+    p->rri_smooth = (truncation == HX_TRUNC_SMOOTH_R4)
+        ? static_cast<float>(std::pow(static_cast<double>(h), -2)) : 0.f;
+    for (unsigned i = 0; i < ntype1 * ntype2; ++i) {
+        float eps = epsilon[i];
+        float sigma2 = sigma[i] * sigma[i];
+        float r_cut = sigma[i] * cutoff_sigma[i];
+        float rr_cut = r_cut * r_cut;
+        // host-side operator() of the float potential, evaluated at rr_cut
+        float rri = sigma2 / rr_cut;
+        float r6i = rri * rri * rri;
+        float eps_r6i = eps * r6i;
+        float en_cut = 4 * eps_r6i * (r6i - 1);
+        p->epsilon[i] = eps;
+        p->sigma2[i] = sigma2;
+        p->r_cut[i] = r_cut;
+        p->rr_cut[i] = rr_cut;
+        p->en_cut[i] = (truncation == HX_TRUNC_SHARP) ? 0.f : en_cut;
+    }
+    return HX_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,429 @@
+// Particle state initialisation, velocity-Verlet (double-single), max-displacement reduction,
+// rand48 and the Andersen thermostat.
+//
+// Reference: halmd/mdsim/gpu/particle.cpp:93-140 (initial values),
+// halmd/mdsim/gpu/integrators/verlet_kernel.cu:37-98, verlet_nvt_andersen_kernel.cu:45-171,
+// halmd/mdsim/gpu/max_displacement_kernel.cu:36-68, halmd/random/gpu/rand48_kernel.{cu,cuh},
+// halmd/random/gpu/normal_distribution.cuh:49-67, halmd/numeric/mp/uint48.hpp:72-111.
+#include "common.cuh"
+
+namespace hx {
+
+// ---- state init ---------------------------------------------------------------------------------------
+__global__ void k_state_init(float4* pos, float4* vel, float4* image, float4* force, unsigned* id, unsigned* rid,
+                             unsigned n, unsigned A)
+{
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A) return;
+    // position (0,0,0) species 0 — ghosts carry species -1U; velocity 0, mass 1 (particle.cpp:93-113)
+    pos[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(i < n ? 0u : HX_PH));
+    pos[i + A] = make_float4(0.f, 0.f, 0.f, 0.f);
+    vel[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+    vel[i + A] = make_float4(0.f, 0.f, 0.f, 0.f);
+    image[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    force[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    id[i] = i;
+    rid[i] = i;
+}
+
+// ---- velocity-Verlet ---------------------------------------------------------------------------------
+struct ds3 { ds x, y, z; };
+
+// v += f * (dt/2) / m        (float product, float division, then double-single add)
+__device__ __forceinline__ void half_kick(ds3& v, float4 f, float half_dt, float mass)
+{
+    v.x = ds_add(v.x, make_ds(__fdiv_rn(__fmul_rn(f.x, half_dt), mass)));
+    v.y = ds_add(v.y, make_ds(__fdiv_rn(__fmul_rn(f.y, half_dt), mass)));
+    v.z = ds_add(v.z, make_ds(__fdiv_rn(__fmul_rn(f.z, half_dt), mass)));
+}
+
+// r += v * dt;  image = rint(r_hi / L);  r -= image * L      (verlet_kernel.cu:60-62, box_kernel.cuh:37-45)
+__device__ __forceinline__ float drift_wrap(ds& r, ds v, float dt, float L)
+{
+    r = ds_add(r, ds_mul(v, make_ds(dt)));
+    float image = rintf(__fdiv_rn(r.hi, L));
+    r = ds_sub(r, make_ds(__fmul_rn(image, L)));
+    return image;
+}
+
+template <bool FINALIZE, bool INTEGRATE>
+__global__ void __launch_bounds__(128) k_verlet(float4* __restrict__ pos, float4* __restrict__ image,
+                                               float4* __restrict__ vel, const float4* __restrict__ force,
+                                               unsigned n, unsigned A, float dt, vec3 L, vec3 invL,
+                                               const float4* __restrict__ r0, unsigned* __restrict__ ctl)
+{
+    if (ctl && ctl[CTL_HALTED]) return;
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    float rr = 0.f;
+    if (i < A) {
+        float4 vh = vel[i], vl = vel[i + A];
+        float4 f = force[i];
+        float const mass = vh.w;
+        float const half_dt = __fmul_rn(dt, 0.5f);      // timestep / 2 in float (verlet_kernel.cu:59)
+        ds3 v = {make_ds(vh.x, vl.x), make_ds(vh.y, vl.y), make_ds(vh.z, vl.z)};
+        if (FINALIZE) half_kick(v, f, half_dt, mass);
+        if (INTEGRATE) {
+            half_kick(v, f, half_dt, mass);
+            float4 ph = pos[i], pl = pos[i + A];
+            ds rx = make_ds(ph.x, pl.x), ry = make_ds(ph.y, pl.y), rz = make_ds(ph.z, pl.z);
+            float ix = drift_wrap(rx, v.x, dt, L.x);
+            float iy = drift_wrap(ry, v.y, dt, L.y);
+            float iz = drift_wrap(rz, v.z, dt, L.z);
+            pos[i] = make_float4(rx.hi, ry.hi, rz.hi, ph.w);
+            pos[i + A] = make_float4(rx.lo, ry.lo, rz.lo, 0.f);
+            if (!(ix == 0.f && iy == 0.f && iz == 0.f)) {
+                float4 im = image[i];
+                image[i] = make_float4(__fadd_rn(ix, im.x), __fadd_rn(iy, im.y), __fadd_rn(iz, im.z), 0.f);
+            }
+            if (r0 && i < n) {
+                // max_displacement_kernel.cu:50-58 on the new high words
+                float4 q = r0[i];
+                float dx = minimg(__fsub_rn(rx.hi, q.x), L.x, invL.x);
+                float dy = minimg(__fsub_rn(ry.hi, q.y), L.y, invL.y);
+                float dz = minimg(__fsub_rn(rz.hi, q.z), L.z, invL.z);
+                rr = norm2(dx, dy, dz);
+            }
+        }
+        vel[i] = make_float4(v.x.hi, v.y.hi, v.z.hi, mass);
+        vel[i + A] = make_float4(v.x.lo, v.y.lo, v.z.lo, 0.f);
+    }
+    if (INTEGRATE && r0) {
+        rr = warp_max(rr);
+        if ((threadIdx.x & 31u) == 0 && rr > 0.f) atomicMax(&ctl[CTL_MAX_RR], __float_as_uint(rr));
+    }
+}
+
+// ---- max displacement (stand-alone) --------------------------------------------------------------------
+__global__ void k_displacement(const float4* __restrict__ pos, const float4* __restrict__ r0, unsigned n, vec3 L,
+                               vec3 invL, unsigned* __restrict__ max_rr_bits)
+{
+    float rr = 0.f;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 p = pos[i], q = r0[i];
+        float dx = minimg(__fsub_rn(p.x, q.x), L.x, invL.x);
+        float dy = minimg(__fsub_rn(p.y, q.y), L.y, invL.y);
+        float dz = minimg(__fsub_rn(p.z, q.z), L.z, invL.z);
+        rr = fmaxf(rr, norm2(dx, dy, dz));
+    }
+    rr = warp_max(rr);
+    if ((threadIdx.x & 31u) == 0 && rr > 0.f) atomicMax(max_rr_bits, __float_as_uint(rr));
+}
+
+// ---- rand48 ---------------------------------------------------------------------------------------------
+constexpr unsigned long long R48_MASK = (1ull << 48) - 1;
+constexpr unsigned long long R48_A = 0x5DEECE66Dull;
+constexpr unsigned long long R48_C = 0xBull;
+
+__host__ __device__ inline unsigned long long r48_pack(const uint16_t* s)
+{
+    return static_cast<unsigned long long>(s[0]) | (static_cast<unsigned long long>(s[1]) << 16)
+           | (static_cast<unsigned long long>(s[2]) << 32);
+}
+
+__host__ __device__ inline void r48_unpack(unsigned long long v, uint16_t* s)
+{
+    s[0] = static_cast<uint16_t>(v & 0xFFFF);
+    s[1] = static_cast<uint16_t>((v >> 16) & 0xFFFF);
+    s[2] = static_cast<uint16_t>((v >> 32) & 0xFFFF);
+}
+
+// thread t starts at x_{t+1} = a^(t+1) x_0 + c (1 + a + ... + a^t)   (rand48_kernel.cu:42-100)
+__global__ void k_rand48_seed(uint16_t* __restrict__ state, unsigned nthreads, unsigned long long x0)
+{
+    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    // (A, C) of the affine map applied t+1 times, by binary exponentiation of (a, c)
+    unsigned long long A = 1, C = 0;           // identity
+    unsigned long long a = R48_A, c = R48_C;   // current power
+    for (unsigned k = t + 1; k > 0; k >>= 1) {
+        if (k & 1u) {
+            // compose: x -> a (A x + C) + c
+            A = (a * A) & R48_MASK;
+            C = (a * C + c) & R48_MASK;
+        }
+        // square: x -> a (a x + c) + c
+        c = (a * c + c) & R48_MASK;
+        a = (a * a) & R48_MASK;
+    }
+    r48_unpack((A * x0 + C) & R48_MASK, state + 3 * t);
+}
+
+struct r48 {
+    unsigned long long s, a, c;
+    // rand48_kernel.cuh:59-65 — variate from the state before advancing
+    __device__ __forceinline__ float uniform()
+    {
+        float z = static_cast<float>((s >> 32) & 0xFFFF), y = static_cast<float>((s >> 16) & 0xFFFF);
+        float u = __fadd_rn(__fmul_rn(z, 1.f / 65536.f), __fmul_rn(y, 1.f / 4294967296.f));
+        s = (a * s + c) & R48_MASK;
+        return u;
+    }
+};
+
+__global__ void k_rand48_uniform(uint16_t* __restrict__ state, unsigned long long a, unsigned long long c,
+                                 float* __restrict__ out, unsigned n)
+{
+    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    r48 g = {r48_pack(state + 3 * t), a, c};
+    for (unsigned i = t; i < n; i += gridDim.x * blockDim.x) out[i] = g.uniform();
+    r48_unpack(g.s, state + 3 * t);
+}
+
+// Box–Muller polar method (normal_distribution.cuh:49-67); the rejection test is evaluated in a fixed
+// operation order so that the CPU oracle consumes the same number of variates.
+__device__ __forceinline__ void normal_pair(r48& g, float sigma, float& n1, float& n2)
+{
+    float v1, v2, s;
+    do {
+        v1 = __fmaf_rn(2.f, g.uniform(), -1.f);
+        v2 = __fmaf_rn(2.f, g.uniform(), -1.f);
+        s = __fmaf_rn(v1, v1, __fmul_rn(v2, v2));
+    } while (s >= 1.f);
+    float w = sigma * sqrtf(-2.f * logf(s) / s);
+    n1 = w * v1;
+    n2 = w * v2;
+}
+
+// verlet_nvt_andersen_kernel.cu:96-171 — launched with the RNG's grid (blocks x threads); the warp-wide
+// collision decision and the grid-stride particle mapping are part of the algorithm's definition.
+__global__ void k_andersen_finalize(float4* __restrict__ vel, const float4* __restrict__ force, unsigned n, unsigned A,
+                                    float dt, float sqrt_temperature, float q, uint16_t* __restrict__ state,
+                                    unsigned long long ra, unsigned long long rc, const unsigned* __restrict__ ctl)
+{
+    if (ctl && ctl[CTL_HALTED]) return;
+    unsigned const t = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned const T = gridDim.x * blockDim.x;
+    r48 g = {r48_pack(state + 3 * t), ra, rc};
+    bool cached = false;
+    float cache = 0.f;
+    float const half_dt = __fmul_rn(dt, 0.5f);
+    // all lanes of a warp must take part in the vote: iterate over whole warps
+    unsigned const warp_base = t & ~31u;
+    for (unsigned base = warp_base; base < n; base += T) {
+        unsigned i = base + (t & 31u);
+        bool const valid = i < n;
+        // lanes beyond n left the loop in the reference (`i < npart`); they do not vote and draw nothing
+        unsigned const active = __ballot_sync(0xFFFFFFFFu, valid);
+        if (!valid) continue;
+        float4 vh = vel[i], vl = vel[i + A];
+        float const mass = vh.w;
+        bool const no_coll = g.uniform() > q;
+        if (__all_sync(active, no_coll)) {
+            float4 f = force[i];
+            ds3 v = {make_ds(vh.x, vl.x), make_ds(vh.y, vl.y), make_ds(vh.z, vl.z)};
+            half_kick(v, f, half_dt, mass);
+            vel[i] = make_float4(v.x.hi, v.y.hi, v.z.hi, mass);
+            vel[i + A] = make_float4(v.x.lo, v.y.lo, v.z.lo, 0.f);
+        } else {
+            float vx, vy, vz;
+            normal_pair(g, sqrt_temperature, vx, vy);
+            if ((cached = !cached)) {
+                normal_pair(g, sqrt_temperature, vz, cache);
+            } else {
+                vz = cache;
+            }
+            vel[i] = make_float4(vx, vy, vz, mass);
+            vel[i + A] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    r48_unpack(g.s, state + 3 * t);
+}
+
+} // namespace hx
+
+using namespace hx;
+
+extern "C" {
+
+int hx_state_init(hx_float4* position_dev, hx_float4* velocity_dev, hx_float4* image_dev, hx_float4* force_dev,
+                  uint32_t* id_dev, uint32_t* reverse_id_dev, size_t nparticle, size_t array_size, void* stream)
+{
+    if (!position_dev || !velocity_dev || !image_dev || !force_dev || !id_dev || !reverse_id_dev
+        || nparticle > array_size || array_size == 0 || array_size >= 0x7FFFFFFFull) {
+        set_error("hx_state_init: invalid argument");
+        return HX_E_INVALID;
+    }
+    k_state_init<<<div_up(array_size, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<float4*>(position_dev), reinterpret_cast<float4*>(velocity_dev),
+        reinterpret_cast<float4*>(image_dev), reinterpret_cast<float4*>(force_dev), id_dev, reverse_id_dev,
+        static_cast<unsigned>(nparticle), static_cast<unsigned>(array_size));
+    return check_launch("k_state_init");
+}
+
+static int verlet_launch(bool fin, bool integ, hx_float4* pos, hx_float4* image, hx_float4* vel,
+                         const hx_float4* force, size_t n, size_t A, float dt, const float L[3],
+                         const hx_float4* r0, uint32_t* ctl, void* stream)
+{
+    if (!vel || !force || A == 0 || A >= 0x7FFFFFFFull || n > A || (integ && (!pos || !image || !L))
+        || (r0 && !ctl)) {
+        set_error("hx_verlet: invalid argument");
+        return HX_E_INVALID;
+    }
+    vec3 Lv = {1.f, 1.f, 1.f}, iLv = {1.f, 1.f, 1.f};
+    if (L) {
+        Lv = make_vec3(L);
+        iLv = {1.0f / L[0], 1.0f / L[1], 1.0f / L[2]};
+    }
+    dim3 grid(div_up(A, 128)), block(128);
+    cudaStream_t st = as_stream(stream);
+    float4* p = reinterpret_cast<float4*>(pos);
+    float4* im = reinterpret_cast<float4*>(image);
+    float4* v = reinterpret_cast<float4*>(vel);
+    const float4* f = reinterpret_cast<const float4*>(force);
+    const float4* q = reinterpret_cast<const float4*>(r0);
+    unsigned nn = static_cast<unsigned>(n), AA = static_cast<unsigned>(A);
+    if (fin && integ) k_verlet<true, true><<<grid, block, 0, st>>>(p, im, v, f, nn, AA, dt, Lv, iLv, q, ctl);
+    else if (integ) k_verlet<false, true><<<grid, block, 0, st>>>(p, im, v, f, nn, AA, dt, Lv, iLv, q, ctl);
+    else k_verlet<true, false><<<grid, block, 0, st>>>(p, im, v, f, nn, AA, dt, Lv, iLv, q, ctl);
+    return check_launch("k_verlet");
+}
+
+int hx_verlet_integrate(hx_float4* position_dev, hx_float4* image_dev, hx_float4* velocity_dev,
+                        const hx_float4* force_dev, size_t array_size, float timestep, const float box_length[3],
+                        void* stream)
+{
+    return verlet_launch(false, true, position_dev, image_dev, velocity_dev, force_dev, array_size, array_size,
+                         timestep, box_length, nullptr, nullptr, stream);
+}
+
+int hx_verlet_finalize(hx_float4* velocity_dev, const hx_float4* force_dev, size_t array_size, float timestep,
+                       void* stream)
+{
+    return verlet_launch(true, false, nullptr, nullptr, velocity_dev, force_dev, array_size, array_size, timestep,
+                         nullptr, nullptr, nullptr, stream);
+}
+
+int hx_verlet_finalize_integrate(hx_float4* position_dev, hx_float4* image_dev, hx_float4* velocity_dev,
+                                 const hx_float4* force_dev, size_t nparticle, size_t array_size, float timestep,
+                                 const float box_length[3], int do_finalize, const hx_float4* r0_dev,
+                                 uint32_t* ctl_dev, void* stream)
+{
+    return verlet_launch(do_finalize != 0, true, position_dev, image_dev, velocity_dev, force_dev, nparticle,
+                         array_size, timestep, box_length, r0_dev, ctl_dev, stream);
+}
+
+int hx_verlet_finalize_guarded(hx_float4* velocity_dev, const hx_float4* force_dev, size_t array_size,
+                               float timestep, uint32_t* ctl_dev, void* stream)
+{
+    return verlet_launch(true, false, nullptr, nullptr, velocity_dev, force_dev, array_size, array_size, timestep,
+                         nullptr, nullptr, ctl_dev, stream);
+}
+
+int hx_ctl_reset(uint32_t* ctl_dev, void* stream)
+{
+    if (!ctl_dev) { set_error("hx_ctl_reset: null pointer"); return HX_E_INVALID; }
+    cudaError_t err = cudaMemsetAsync(ctl_dev, 0, 4 * sizeof(uint32_t), as_stream(stream));
+    if (err != cudaSuccess) { set_error("hx_ctl_reset: %s", cudaGetErrorString(err)); return static_cast<int>(err); }
+    return HX_OK;
+}
+
+int hx_displacement_zero(const hx_float4* position_hi_dev, hx_float4* r0_dev, size_t nparticle, void* stream)
+{
+    if (!position_hi_dev || !r0_dev) { set_error("hx_displacement_zero: null pointer"); return HX_E_INVALID; }
+    cudaError_t err = cudaMemcpyAsync(r0_dev, position_hi_dev, nparticle * sizeof(hx_float4),
+                                      cudaMemcpyDeviceToDevice, as_stream(stream));
+    if (err != cudaSuccess) { set_error("hx_displacement_zero: %s", cudaGetErrorString(err)); return static_cast<int>(err); }
+    return HX_OK;
+}
+
+int hx_displacement_max(const hx_float4* position_hi_dev, const hx_float4* r0_dev, size_t nparticle,
+                        const float box_length[3], uint32_t* max_rr_bits_dev, int reset, void* stream)
+{
+    if (!position_hi_dev || !r0_dev || !box_length || !max_rr_bits_dev || nparticle >= 0x7FFFFFFFull) {
+        set_error("hx_displacement_max: invalid argument");
+        return HX_E_INVALID;
+    }
+    cudaStream_t st = as_stream(stream);
+    if (reset) {
+        cudaError_t err = cudaMemsetAsync(max_rr_bits_dev, 0, sizeof(uint32_t), st);
+        if (err != cudaSuccess) { set_error("hx_displacement_max: %s", cudaGetErrorString(err)); return static_cast<int>(err); }
+    }
+    if (nparticle == 0) return HX_OK;
+    vec3 L = make_vec3(box_length);
+    vec3 iL = {1.0f / box_length[0], 1.0f / box_length[1], 1.0f / box_length[2]};
+    unsigned blocks = div_up(nparticle, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_displacement<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(position_hi_dev),
+                                          reinterpret_cast<const float4*>(r0_dev), static_cast<unsigned>(nparticle),
+                                          L, iL, max_rr_bits_dev);
+    return check_launch("k_displacement");
+}
+
+int hx_rand48_seed(hx_rand48* rng, unsigned blocks, unsigned threads, unsigned seed, uint16_t* state_dev,
+                   void* stream)
+{
+    if (!rng || !state_dev || blocks == 0 || threads == 0 || threads % 32 != 0 || threads > 1024) {
+        set_error("hx_rand48_seed: invalid argument");
+        return HX_E_INVALID;
+    }
+    unsigned const T = blocks * threads;
+    rng->blocks = blocks;
+    rng->threads = threads;
+    // leapfrog constants: the affine map applied T times (rand48_kernel.cu:78-82, thread GTDIM-1)
+    unsigned long long A = 1, C = 0, a = R48_A, c = R48_C;
+    for (unsigned k = T; k > 0; k >>= 1) {
+        if (k & 1u) {
+            A = (a * A) & R48_MASK;
+            C = (a * C + c) & R48_MASK;
+        }
+        c = (a * c + c) & R48_MASK;
+        a = (a * a) & R48_MASK;
+    }
+    r48_unpack(A, rng->a);
+    r48_unpack(C, rng->c);
+    // default seed words (0x330E, 0xABCD, 0x1234); a non-zero seed replaces the upper two (rand48_kernel.cu:85-92)
+    uint16_t x[3] = {0x330E, 0xABCD, 0x1234};
+    if (seed > 0) {
+        x[1] = seed & 0xFFFF;
+        x[2] = (seed >> 16) & 0xFFFF;
+    }
+    k_rand48_seed<<<blocks, threads, 0, as_stream(stream)>>>(state_dev, T, r48_pack(x));
+    return check_launch("k_rand48_seed");
+}
+
+int hx_rand48_uniform(const hx_rand48* rng, uint16_t* state_dev, float* out_dev, size_t n, void* stream)
+{
+    if (!rng || !state_dev || !out_dev || n >= 0x7FFFFFFFull) {
+        set_error("hx_rand48_uniform: invalid argument");
+        return HX_E_INVALID;
+    }
+    k_rand48_uniform<<<rng->blocks, rng->threads, 0, as_stream(stream)>>>(state_dev, r48_pack(rng->a), r48_pack(rng->c),
+                                                                         out_dev, static_cast<unsigned>(n));
+    return check_launch("k_rand48_uniform");
+}
+
+static int andersen_launch(hx_float4* velocity_dev, const hx_float4* force_dev, size_t nparticle, size_t array_size,
+                           float timestep, float sqrt_temperature, float coll_prob, const hx_rand48* rng,
+                           uint16_t* state_dev, const uint32_t* ctl, void* stream)
+{
+    if (!velocity_dev || !force_dev || !rng || !state_dev || nparticle > array_size || array_size >= 0x7FFFFFFFull) {
+        set_error("hx_andersen_finalize: invalid argument");
+        return HX_E_INVALID;
+    }
+    // pow(1 - q, warpSize) = 1 - coll_prob  (verlet_nvt_andersen_kernel.cu:121-123); evaluated on the host in
+    // IEEE float instead of the device's __powf approximation
+    float q = 1.f - powf(1.f - coll_prob, 1.f / 32);
+    k_andersen_finalize<<<rng->blocks, rng->threads, 0, as_stream(stream)>>>(
+        reinterpret_cast<float4*>(velocity_dev), reinterpret_cast<const float4*>(force_dev),
+        static_cast<unsigned>(nparticle), static_cast<unsigned>(array_size), timestep, sqrt_temperature, q, state_dev,
+        r48_pack(rng->a), r48_pack(rng->c), ctl);
+    return check_launch("k_andersen_finalize");
+}
+
+int hx_andersen_finalize(hx_float4* velocity_dev, const hx_float4* force_dev, size_t nparticle, size_t array_size,
+                         float timestep, float sqrt_temperature, float coll_prob, const hx_rand48* rng,
+                         uint16_t* state_dev, void* stream)
+{
+    return andersen_launch(velocity_dev, force_dev, nparticle, array_size, timestep, sqrt_temperature, coll_prob, rng,
+                           state_dev, nullptr, stream);
+}
+
+int hx_andersen_finalize_guarded(hx_float4* velocity_dev, const hx_float4* force_dev, size_t nparticle,
+                                 size_t array_size, float timestep, float sqrt_temperature, float coll_prob,
+                                 const hx_rand48* rng, uint16_t* state_dev, const uint32_t* ctl_dev, void* stream)
+{
+    return andersen_launch(velocity_dev, force_dev, nparticle, array_size, timestep, sqrt_temperature, coll_prob, rng,
+                           state_dev, ctl_dev, stream);
+}
+
+} // extern "C"

@@ -1,0 +1,293 @@
+// Observables on the hot path: unfolded samples in id order, block MSD, density modes, thermodynamic sums.
+//
+// Reference: halmd/observables/gpu/phase_space_kernel.cu:39-66; halmd/observables/gpu/dynamics/
+// mean_square_displacement.cpp:55-68 with tagged_particle.hpp:33-61 and halmd/numeric/accumulator.hpp:56-132;
+// halmd/observables/gpu/density_mode_kernel.cu:46-108; halmd/observables/gpu/thermodynamics_kernel.cu:35-97.
+//
+// The reference launches one 32x256 reduction (+ blocking D2H) per lag time; here one launch correlates the
+// first sample of a block with all `nlags` later samples and leaves (count, mean, M2) triples in device memory.
+#include "common.cuh"
+
+namespace hx {
+
+__global__ void k_sample_positions(const float4* __restrict__ pos, const float4* __restrict__ image,
+                                   const unsigned* __restrict__ rid, unsigned n, vec3 L, float4* __restrict__ out)
+{
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned r = rid[i];
+    float4 p = __ldg(&pos[r]);
+    float4 im = __ldg(&image[r]);
+    // extend_periodic: r += image * L, contracted to FMA by nvcc in the reference (box_kernel.cuh:54-61)
+    out[i] = make_float4(__fmaf_rn(im.x, L.x, p.x), __fmaf_rn(im.y, L.y, p.y), __fmaf_rn(im.z, L.z, p.z), p.w);
+}
+
+__global__ void k_sample_velocities(const float4* __restrict__ vel, const unsigned* __restrict__ rid, unsigned n,
+                                    float4* __restrict__ out)
+{
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = __ldg(&vel[rid[i]]);
+}
+
+// Welford / Chan accumulators in double
+struct wf { double n, m, v; };
+
+__device__ __forceinline__ void wf_add(wf& a, double x)
+{
+    double t = x - a.m;
+    a.n += 1.0;
+    a.m += t / a.n;
+    a.v += t * (x - a.m);
+}
+
+__device__ __forceinline__ void wf_merge(wf& a, wf const& b)
+{
+    // accumulator.hpp:104-118
+    if (b.n > 0) {
+        double count = a.n + b.n;
+        double diff = a.m - b.m;
+        a.v += b.v + diff * diff * a.n * b.n / count;
+        a.m = (a.n * a.m + b.n * b.m) / count;
+        a.n = count;
+    }
+}
+
+__device__ __forceinline__ wf wf_shfl_xor(wf a, int o)
+{
+    wf b;
+    b.n = __shfl_xor_sync(0xFFFFFFFFu, a.n, o);
+    b.m = __shfl_xor_sync(0xFFFFFFFFu, a.m, o);
+    b.v = __shfl_xor_sync(0xFFFFFFFFu, a.v, o);
+    return b;
+}
+
+constexpr unsigned MSD_BLOCKS = 128;
+constexpr unsigned MSD_THREADS = 256;
+
+// grid = (MSD_BLOCKS, nlags): block accumulators → partial[(lag * MSD_BLOCKS + block)]
+__global__ void k_msd_partial(const float4* __restrict__ first, const float4* const* __restrict__ samples, unsigned n,
+                              wf* __restrict__ partial)
+{
+    __shared__ wf s_w[MSD_THREADS / 32];
+    const float4* second = samples[blockIdx.y];
+    wf acc = {0., 0., 0.};
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 a = first[i], b = second[i];
+        // mean_square_displacement.hpp:35-41: dr = r2 - r1; inner_prod(dr, dr) in float
+        float dx = __fsub_rn(b.x, a.x), dy = __fsub_rn(b.y, a.y), dz = __fsub_rn(b.z, a.z);
+        wf_add(acc, static_cast<double>(norm2(dx, dy, dz)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        wf b = wf_shfl_xor(acc, o);
+        // merge in a lane-symmetric way so that all lanes end with the same value
+        wf lo = (threadIdx.x & o) ? b : acc, hi = (threadIdx.x & o) ? acc : b;
+        wf_merge(lo, hi);
+        acc = lo;
+    }
+    if ((threadIdx.x & 31u) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        wf t = s_w[0];
+        for (unsigned w = 1; w < MSD_THREADS / 32; ++w) wf_merge(t, s_w[w]);
+        partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+__global__ void k_msd_final(const wf* __restrict__ partial, unsigned nblocks, double* __restrict__ out)
+{
+    unsigned lag = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    wf t = partial[lag * nblocks];
+    for (unsigned b = 1; b < nblocks; ++b) wf_merge(t, partial[lag * nblocks + b]);
+    out[3 * lag + 0] = t.n;
+    out[3 * lag + 1] = t.m;
+    out[3 * lag + 2] = t.v;
+}
+
+// density modes: block (x) strides over particles, loops over a tile of wavevectors held in registers
+constexpr unsigned DM_THREADS = 256;
+constexpr unsigned DM_QTILE = 8;
+
+__global__ void k_density_modes(const float4* __restrict__ pos, unsigned n, const float* __restrict__ q, unsigned nq,
+                                double* __restrict__ rho)
+{
+    __shared__ double s_c[DM_THREADS / 32][DM_QTILE], s_s[DM_THREADS / 32][DM_QTILE];
+    unsigned const q0 = blockIdx.y * DM_QTILE;
+    float qx[DM_QTILE], qy[DM_QTILE], qz[DM_QTILE];
+    double c[DM_QTILE], s[DM_QTILE];
+#pragma unroll
+    for (unsigned k = 0; k < DM_QTILE; ++k) {
+        bool ok = q0 + k < nq;
+        qx[k] = ok ? q[3 * (q0 + k) + 0] : 0.f;
+        qy[k] = ok ? q[3 * (q0 + k) + 1] : 0.f;
+        qz[k] = ok ? q[3 * (q0 + k) + 2] : 0.f;
+        c[k] = 0.;
+        s[k] = 0.;
+    }
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 p = pos[i];
+#pragma unroll
+        for (unsigned k = 0; k < DM_QTILE; ++k) {
+            // inner_prod(q, r) in the reference's compiled order, then accurate sincos
+            float qr = __fmaf_rn(qz[k], p.z, __fmaf_rn(qx[k], p.x, __fmul_rn(qy[k], p.y)));
+            float sn, cs;
+            sincosf(qr, &sn, &cs);
+            c[k] += cs;
+            s[k] += sn;
+        }
+    }
+#pragma unroll
+    for (unsigned k = 0; k < DM_QTILE; ++k) {
+        c[k] = warp_sum(c[k]);
+        s[k] = warp_sum(s[k]);
+    }
+    if ((threadIdx.x & 31u) == 0) {
+#pragma unroll
+        for (unsigned k = 0; k < DM_QTILE; ++k) {
+            s_c[threadIdx.x >> 5][k] = c[k];
+            s_s[threadIdx.x >> 5][k] = s[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < DM_QTILE && q0 + threadIdx.x < nq) {
+        double cc = 0., ss = 0.;
+        for (unsigned w = 0; w < DM_THREADS / 32; ++w) {
+            cc += s_c[w][threadIdx.x];
+            ss += s_s[w][threadIdx.x];
+        }
+        // (sum cos, -sum sin): density_mode.cpp:126-129
+        atomicAdd(&rho[2 * (q0 + threadIdx.x) + 0], cc);
+        atomicAdd(&rho[2 * (q0 + threadIdx.x) + 1], -ss);
+    }
+}
+
+constexpr unsigned TH_THREADS = 256;
+
+__global__ void k_thermodynamics(const float4* __restrict__ vel, const float* __restrict__ en_pot,
+                                 const float* __restrict__ stress, size_t stress_stride, unsigned n,
+                                 double* __restrict__ out)
+{
+    __shared__ double s_red[TH_THREADS / 32][7];
+    double acc[7] = {0., 0., 0., 0., 0., 0., 0.};
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 v = vel[i];
+        // mass * inner_prod(v, v) in float (thermodynamics_kernel.cu:35-41)
+        acc[0] += static_cast<double>(__fmul_rn(v.w, norm2(v.x, v.y, v.z)));
+        acc[1] += static_cast<double>(__fmul_rn(v.w, v.x));
+        acc[2] += static_cast<double>(__fmul_rn(v.w, v.y));
+        acc[3] += static_cast<double>(__fmul_rn(v.w, v.z));
+        acc[4] += static_cast<double>(v.w);
+        if (en_pot) acc[5] += static_cast<double>(en_pot[i]);
+        if (stress) {
+            acc[6] += static_cast<double>(stress[i]) + static_cast<double>(stress[stress_stride + i])
+                      + static_cast<double>(stress[2 * stress_stride + i]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) acc[k] = warp_sum(acc[k]);
+    if ((threadIdx.x & 31u) == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) s_red[threadIdx.x >> 5][k] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double t = 0.;
+        for (unsigned w = 0; w < TH_THREADS / 32; ++w) t += s_red[w][threadIdx.x];
+        atomicAdd(&out[threadIdx.x], t);
+    }
+}
+
+} // namespace hx
+
+using namespace hx;
+
+extern "C" {
+
+int hx_sample_positions(const hx_float4* position_hi_dev, const hx_float4* image_dev, const uint32_t* reverse_id_dev,
+                        size_t nparticle, const float box_length[3], hx_float4* sample_dev, void* stream)
+{
+    if (!position_hi_dev || !image_dev || !reverse_id_dev || !box_length || !sample_dev || nparticle >= 0x7FFFFFFFull) {
+        set_error("hx_sample_positions: invalid argument");
+        return HX_E_INVALID;
+    }
+    if (nparticle == 0) return HX_OK;
+    k_sample_positions<<<div_up(nparticle, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(position_hi_dev), reinterpret_cast<const float4*>(image_dev), reverse_id_dev,
+        static_cast<unsigned>(nparticle), make_vec3(box_length), reinterpret_cast<float4*>(sample_dev));
+    return check_launch("k_sample_positions");
+}
+
+int hx_sample_velocities(const hx_float4* velocity_hi_dev, const uint32_t* reverse_id_dev, size_t nparticle,
+                         hx_float4* sample_dev, void* stream)
+{
+    if (!velocity_hi_dev || !reverse_id_dev || !sample_dev || nparticle >= 0x7FFFFFFFull) {
+        set_error("hx_sample_velocities: invalid argument");
+        return HX_E_INVALID;
+    }
+    if (nparticle == 0) return HX_OK;
+    k_sample_velocities<<<div_up(nparticle, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(velocity_hi_dev), reverse_id_dev, static_cast<unsigned>(nparticle),
+        reinterpret_cast<float4*>(sample_dev));
+    return check_launch("k_sample_velocities");
+}
+
+size_t hx_msd_scratch_bytes(unsigned nlags) { return static_cast<size_t>(nlags) * MSD_BLOCKS * sizeof(wf); }
+
+int hx_msd_block(const hx_float4* first_dev, const hx_float4* const* samples_dev, unsigned nlags, size_t nparticle,
+                 double* out_dev, void* scratch_dev, size_t scratch_bytes, void* stream)
+{
+    if (!first_dev || !samples_dev || !out_dev || !scratch_dev || nlags == 0 || nlags > 65535
+        || scratch_bytes < hx_msd_scratch_bytes(nlags) || nparticle >= 0x7FFFFFFFull) {
+        set_error("hx_msd_block: invalid argument");
+        return HX_E_INVALID;
+    }
+    cudaStream_t st = as_stream(stream);
+    wf* partial = static_cast<wf*>(scratch_dev);
+    k_msd_partial<<<dim3(MSD_BLOCKS, nlags), MSD_THREADS, 0, st>>>(
+        reinterpret_cast<const float4*>(first_dev), reinterpret_cast<const float4* const*>(samples_dev),
+        static_cast<unsigned>(nparticle), partial);
+    int rc = check_launch("k_msd_partial");
+    if (rc) return rc;
+    k_msd_final<<<nlags, 32, 0, st>>>(partial, MSD_BLOCKS, out_dev);
+    return check_launch("k_msd_final");
+}
+
+int hx_density_modes(const hx_float4* position_hi_dev, size_t nparticle, const float* q_dev, unsigned nq,
+                     double* rho_dev, void* stream)
+{
+    if (!position_hi_dev || !q_dev || !rho_dev || nq == 0 || nparticle >= 0x7FFFFFFFull) {
+        set_error("hx_density_modes: invalid argument");
+        return HX_E_INVALID;
+    }
+    cudaStream_t st = as_stream(stream);
+    cudaError_t err = cudaMemsetAsync(rho_dev, 0, 2 * static_cast<size_t>(nq) * sizeof(double), st);
+    if (err != cudaSuccess) { set_error("hx_density_modes: %s", cudaGetErrorString(err)); return static_cast<int>(err); }
+    if (nparticle == 0) return HX_OK;
+    unsigned bx = div_up(nparticle, DM_THREADS);
+    if (bx > 296) bx = 296;
+    k_density_modes<<<dim3(bx, div_up(nq, DM_QTILE)), DM_THREADS, 0, st>>>(
+        reinterpret_cast<const float4*>(position_hi_dev), static_cast<unsigned>(nparticle), q_dev, nq, rho_dev);
+    return check_launch("k_density_modes");
+}
+
+int hx_thermodynamics(const hx_float4* velocity_hi_dev, const float* en_pot_dev, const float* stress_dev,
+                      size_t stress_stride, size_t nparticle, double* out_dev, void* stream)
+{
+    if (!velocity_hi_dev || !out_dev || nparticle >= 0x7FFFFFFFull) {
+        set_error("hx_thermodynamics: invalid argument");
+        return HX_E_INVALID;
+    }
+    cudaStream_t st = as_stream(stream);
+    cudaError_t err = cudaMemsetAsync(out_dev, 0, 8 * sizeof(double), st);
+    if (err != cudaSuccess) { set_error("hx_thermodynamics: %s", cudaGetErrorString(err)); return static_cast<int>(err); }
+    if (nparticle == 0) return HX_OK;
+    unsigned blocks = div_up(nparticle, TH_THREADS);
+    if (blocks > 296) blocks = 296;
+    k_thermodynamics<<<blocks, TH_THREADS, 0, st>>>(reinterpret_cast<const float4*>(velocity_hi_dev), en_pot_dev,
+                                                   stress_dev, stress_stride, static_cast<unsigned>(nparticle), out_dev);
+    return check_launch("k_thermodynamics");
+}
+
+} // extern "C"

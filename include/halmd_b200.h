@@ -1,0 +1,261 @@
+/*
+ * halmd_b200.h — C ABI of the Blackwell-native MD step loop (kernel level).
+ *
+ * Every entry point replaces one call site where a HALMD host class invokes its
+ * `*_wrapper::kernel.<fn>` cuda::function (layer L3→L2 of the reference).  The
+ * reference interface that each function stands in for is cited as
+ * `file:line` relative to the halmd-org/halmd source tree.
+ *
+ * Conventions
+ *  - plain C types only; all pointers marked `_dev` are device pointers owned by
+ *    the caller; `stream` is a `cudaStream_t` passed as `void*` (NULL = default);
+ *  - every call is asynchronous on `stream`; there are no hidden device syncs;
+ *  - return value: 0 = ok, >0 = cudaError_t of the failed launch/runtime call,
+ *    <0 = contract violation (HX_E_*); `hx_last_error_string()` gives the text;
+ *  - overflow of cell / neighbour placeholders is reported through device-side
+ *    int flags (0 = ok, 1 = overcrowded), never handled behind the caller's back
+ *    (retry contract of halmd/mdsim/gpu/binning.cpp:173-220 and
+ *    halmd/mdsim/gpu/neighbours/from_binning.cpp:185-281);
+ *  - particle state uses HALMD's packing (halmd/mdsim/gpu/particle.cpp:56-160,
+ *    halmd/utility/gpu/dsfloat_cuda_vector.hpp:30-100): `position` and
+ *    `velocity` are float4[2*A] — high words (x,y,z,tag) in [0,A), low words
+ *    (x,y,z,0) in [A,2A); tag = species bits / mass; slots >= n are ghosts with
+ *    species 0xFFFFFFFF.
+ */
+#ifndef HALMD_B200_H
+#define HALMD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HX_PLACEHOLDER 0xFFFFFFFFu
+
+/* error codes (<0: contract violations) */
+#define HX_OK 0
+#define HX_E_INVALID (-1)   /* invalid argument */
+#define HX_E_UNSUPPORTED (-2)
+#define HX_E_NOGPU (-3)     /* no CUDA device / extension unusable: never falls back to CPU */
+
+/* neighbour-list memory layouts (halmd/mdsim/gpu/neighbours/from_binning_kernel.cu:145-149) */
+#define HX_LAYOUT_COLUMN 0  /* g_neighbour[k * stride + i]  (reference default)          */
+#define HX_LAYOUT_ROW    1  /* g_neighbour[i * stride + k]  (reference "unroll_force_loop",
+                               stride = row pitch >= size)                               */
+
+/* potential truncations (halmd/mdsim/gpu/potentials/pair/truncations/) */
+#define HX_TRUNC_SHARP     0
+#define HX_TRUNC_SHIFTED   1
+#define HX_TRUNC_SMOOTH_R4 2
+
+#define HX_MAX_PAIR_TYPES 16 /* ntype1*ntype2 <= 16 */
+
+typedef struct hx_float4 { float x, y, z, w; } hx_float4;
+
+/* ---- library -------------------------------------------------------------------------- */
+int hx_version(void);
+const char* hx_last_error_string(void);
+/* number of CUDA devices visible, or HX_E_NOGPU */
+int hx_device_count(void);
+/* kernels launched by this library since load (all streams); used for `gpu_launches` */
+uint64_t hx_launch_count(void);
+
+/* ---- a1: particle container ------------------------------------------------------------
+ * halmd/mdsim/gpu/particle.cpp:69-113 — array_size = n rounded up to 1024; initial values. */
+size_t hx_array_size(size_t nparticle);
+int hx_state_init(hx_float4* position_dev /*2A*/, hx_float4* velocity_dev /*2A*/,
+                  hx_float4* image_dev /*A*/, hx_float4* force_dev /*A*/,
+                  uint32_t* id_dev /*A*/, uint32_t* reverse_id_dev /*A*/,
+                  size_t nparticle, size_t array_size, void* stream);
+
+/* ---- a2/a3: cell binning ---------------------------------------------------------------
+ * halmd/mdsim/gpu/binning.cpp:47-116 (sizing), :166-221 (update),
+ * halmd/mdsim/gpu/binning_kernel.cu:34-139. */
+int hx_binning_plan(const double box_length[3], size_t nparticle, float r_cut_max, float skin,
+                    double occupancy, unsigned ncell[3], float cell_length[3],
+                    unsigned* cell_size);
+/* scratch: cell_count_dev[ncells] (overwritten). cell_index_dev (n entries) may be NULL.
+ * g_cell_dev[ncells*cell_size]: ascending particle index per cell, padded with placeholders. */
+int hx_binning_update(const hx_float4* position_hi_dev, size_t nparticle,
+                      const float cell_length[3], const unsigned ncell[3], unsigned cell_size,
+                      uint32_t* g_cell_dev, uint32_t* cell_count_dev, uint32_t* cell_index_dev,
+                      int* overflow_flag_dev, void* stream);
+
+/* ---- a4: Hilbert space-filling-curve order ---------------------------------------------
+ * halmd/mdsim/gpu/sorts/hilbert.cpp:51-54 (depth), :71-117; hilbert_kernel.cu:38-69;
+ * halmd/mdsim/sorts/hilbert_kernel.hpp:70-142,205-230. */
+unsigned hx_hilbert_depth(const double box_length[3]);
+int hx_hilbert_keys(const hx_float4* position_hi_dev, size_t nslots, const float box_length[3],
+                    unsigned depth, uint32_t* keys_dev, void* stream);
+int hx_iota_u32(uint32_t* out_dev, size_t n, void* stream);
+/* stable LSD radix sort of (key,value) pairs, in place (halmd/algorithm/gpu/radix_sort.hpp:94-184).
+ * key_bits: number of significant key bits (rounded up to a multiple of 8, <= 32). */
+size_t hx_sort_scratch_bytes(size_t n);
+int hx_sort_pairs_stable_u32(uint32_t* keys_dev, uint32_t* values_dev, size_t n,
+                             unsigned key_bits, void* scratch_dev, size_t scratch_bytes,
+                             void* stream);
+
+/* ---- a5: particle::rearrange -----------------------------------------------------------
+ * halmd/mdsim/gpu/particle.cpp:173-218, particle_kernel.cu:45-68.
+ * out[i] = in[index[i]] for i < n (identity for n <= i < A) for position (hi,lo),
+ * velocity (hi,lo), image, id; reverse_id_out[id_out[i]] = i.  Force is NOT permuted. */
+int hx_state_permute(const uint32_t* index_dev, size_t nparticle, size_t array_size,
+                     const hx_float4* position_in_dev, hx_float4* position_out_dev,
+                     const hx_float4* velocity_in_dev, hx_float4* velocity_out_dev,
+                     const hx_float4* image_in_dev, hx_float4* image_out_dev,
+                     const uint32_t* id_in_dev, uint32_t* id_out_dev,
+                     uint32_t* reverse_id_out_dev, void* stream);
+
+/* ---- a6: max_displacement --------------------------------------------------------------
+ * halmd/mdsim/gpu/max_displacement.cpp:60-106, max_displacement_kernel.cu:36-68. */
+int hx_displacement_zero(const hx_float4* position_hi_dev, hx_float4* r0_dev, size_t nparticle,
+                         void* stream);
+/* writes max_i |minimg(r_i - r0_i)|^2 as float bits into *max_rr_bits_dev (atomicMax on the
+ * IEEE bit pattern; caller zeroes it, or pass reset=1). sqrt and the comparison with skin/2
+ * are hx_displacement_exceeds(). */
+int hx_displacement_max(const hx_float4* position_hi_dev, const hx_float4* r0_dev,
+                        size_t nparticle, const float box_length[3], uint32_t* max_rr_bits_dev,
+                        int reset, void* stream);
+/* host helper: float(sqrt(rr)) > float(skin/2)  (from_binning.cpp:130-131) */
+int hx_displacement_exceeds(uint32_t max_rr_bits, double skin);
+
+/* ---- a7: Verlet neighbour lists from cells ---------------------------------------------
+ * halmd/mdsim/gpu/neighbours/from_binning.cpp:96-119 (sizing), :162-282 (update),
+ * from_binning_kernel.cu:99-267. */
+int hx_nlist_plan(float r_cut_max, float skin, size_t nparticle2, double box_volume,
+                  double occupancy, unsigned cell_size, unsigned* size);
+/* rr_cut_skin[ntype1*ntype2] = (r_cut + skin)^2 as float.  layout COLUMN: list is memset to
+ * placeholders first, stride = array_size.  layout ROW: stride = pitch (multiple of 32 and
+ * >= size+1 unless fill_all); each row is terminated by placeholders up to the next multiple
+ * of 32 (fill_all=1: up to `stride`).  count_dev (n entries, may be NULL) receives list lengths.
+ * overflow flag is raised when a list reaches `size` entries (from_binning_kernel.cu:263-266). */
+int hx_nlist_build(const uint32_t* g_cell_dev, const unsigned ncell[3], unsigned cell_size,
+                   const hx_float4* position_hi_dev, size_t nparticle,
+                   const float* rr_cut_skin, unsigned ntype1, unsigned ntype2,
+                   const float box_length[3], uint32_t* g_neighbour_dev, unsigned size,
+                   size_t stride, int layout, int fill_all, uint32_t* count_dev,
+                   int* overflow_flag_dev, void* stream);
+
+/* ---- a9-a11: Lennard-Jones potential with truncation ------------------------------------
+ * halmd/mdsim/gpu/potentials/pair/lennard_jones.cpp:44-70, lennard_jones_kernel.hpp:43-56,
+ * truncations/smooth_r4.hpp:55-99, smooth_r4_kernel.cuh:53-76, shifted_kernel.cuh:49-57.
+ * Derived tables are computed in float with the reference's formulas. */
+typedef struct hx_lj_params {
+    unsigned ntype1, ntype2;
+    int truncation;            /* HX_TRUNC_* */
+    float rri_smooth;          /* h^-2 (smooth_r4) */
+    float epsilon[HX_MAX_PAIR_TYPES];
+    float sigma2[HX_MAX_PAIR_TYPES];
+    float r_cut[HX_MAX_PAIR_TYPES];   /* cutoff * sigma */
+    float rr_cut[HX_MAX_PAIR_TYPES];
+    float en_cut[HX_MAX_PAIR_TYPES];  /* U(r_cut), 0 for sharp */
+} hx_lj_params;
+
+int hx_potential_lj_init(hx_lj_params* p, unsigned ntype1, unsigned ntype2, const float* epsilon,
+                         const float* sigma, int truncation, const float* cutoff_sigma, float h);
+
+/* ---- a8: truncated pair force ------------------------------------------------------------
+ * halmd/mdsim/gpu/forces/pair_trunc.hpp:193-337, pair_trunc_kernel.cuh:54-255.
+ * en_pot_dev / stress_dev NULL <=> compute_ (no aux); stress is SoA [6][stress_stride]
+ * (xx,yy,zz,xy,xz,yz; halmd/mdsim/force_kernel.hpp:36-95).  aux_weight is the effective weight
+ * (already halved for particle1 == particle2, pair_trunc.hpp:291-294). */
+int hx_pair_force(const hx_lj_params* potential, const hx_float4* position1_hi_dev,
+                  const hx_float4* position2_hi_dev, const uint32_t* g_neighbour_dev,
+                  unsigned size, size_t stride, int layout, size_t nparticle,
+                  const float box_length[3], int force_zero, float aux_weight,
+                  hx_float4* force_dev, float* en_pot_dev, float* stress_dev,
+                  size_t stress_stride, void* stream);
+/* tuning knob for the ROW layout: lanes cooperating on one particle (2, 4 or 8) */
+int hx_pair_force_set_lanes(int lanes);
+
+/* ---- a12: velocity-Verlet in double-single arithmetic -------------------------------------
+ * halmd/mdsim/gpu/integrators/verlet.cpp:64-121, verlet_kernel.cu:37-98,
+ * halmd/numeric/mp/dsfun.hpp:142-207. */
+int hx_verlet_integrate(hx_float4* position_dev, hx_float4* image_dev, hx_float4* velocity_dev,
+                        const hx_float4* force_dev, size_t array_size, float timestep,
+                        const float box_length[3], void* stream);
+int hx_verlet_finalize(hx_float4* velocity_dev, const hx_float4* force_dev, size_t array_size,
+                       float timestep, void* stream);
+/* fused: finalize(step k) [if do_finalize] + integrate(step k+1) + max-displacement reduction
+ * against r0 (bitwise identical to the separate calls).  ctl_dev is a 4-word control block (see
+ * "step-loop support" below): the kernel exits at once if ctl[1] (halted) is set and folds the
+ * maximum squared displacement into ctl[0].  r0_dev and ctl_dev may be NULL (r0 needs ctl). */
+int hx_verlet_finalize_integrate(hx_float4* position_dev, hx_float4* image_dev,
+                                 hx_float4* velocity_dev, const hx_float4* force_dev,
+                                 size_t nparticle, size_t array_size, float timestep,
+                                 const float box_length[3], int do_finalize,
+                                 const hx_float4* r0_dev, uint32_t* ctl_dev, void* stream);
+int hx_verlet_finalize_guarded(hx_float4* velocity_dev, const hx_float4* force_dev,
+                               size_t array_size, float timestep, uint32_t* ctl_dev, void* stream);
+
+/* ---- a13: Andersen thermostat with rand48 ---------------------------------------------------
+ * halmd/random/gpu/rand48.hpp:57-81, rand48_kernel.cu:42-100, rand48_kernel.cuh:40-79,
+ * halmd/mdsim/gpu/integrators/verlet_nvt_andersen_kernel.cu:96-171. */
+typedef struct hx_rand48 {
+    unsigned blocks, threads;      /* 32 x 256 by default (random/gpu/random.cpp:94-101) */
+    uint16_t a[3], c[3];           /* leapfrog multiplier / addend (x = low word) */
+} hx_rand48;
+/* state_dev: uint16_t[3 * blocks*threads] (ushort3 per RNG thread) */
+int hx_rand48_seed(hx_rand48* rng, unsigned blocks, unsigned threads, unsigned seed,
+                   uint16_t* state_dev, void* stream);
+int hx_rand48_uniform(const hx_rand48* rng, uint16_t* state_dev, float* out_dev, size_t n,
+                      void* stream);
+int hx_andersen_finalize(hx_float4* velocity_dev, const hx_float4* force_dev, size_t nparticle,
+                         size_t array_size, float timestep, float sqrt_temperature,
+                         float coll_prob, const hx_rand48* rng, uint16_t* state_dev,
+                         void* stream);
+
+/* ---- a14-a16: observables -------------------------------------------------------------------
+ * halmd/observables/gpu/phase_space_kernel.cu:39-66 (unfolded positions in id order),
+ * halmd/observables/gpu/dynamics/mean_square_displacement.cpp:55-68 + tagged_particle.hpp,
+ * halmd/observables/gpu/density_mode_kernel.cu:46-108. */
+int hx_sample_positions(const hx_float4* position_hi_dev, const hx_float4* image_dev,
+                        const uint32_t* reverse_id_dev, size_t nparticle,
+                        const float box_length[3], hx_float4* sample_dev, void* stream);
+int hx_sample_velocities(const hx_float4* velocity_hi_dev, const uint32_t* reverse_id_dev,
+                         size_t nparticle, hx_float4* sample_dev, void* stream);
+/* correlate `first` with nlags samples: out_dev[3*l + {0,1,2}] = (count, mean, M2) of
+ * |R_l - R_first|^2 over particles, as doubles (mergeable into accumulator<double>,
+ * halmd/numeric/accumulator.hpp:104-118).  samples_dev: device array of nlags device pointers. */
+size_t hx_msd_scratch_bytes(unsigned nlags);
+int hx_msd_block(const hx_float4* first_dev, const hx_float4* const* samples_dev, unsigned nlags,
+                 size_t nparticle, double* out_dev, void* scratch_dev, size_t scratch_bytes,
+                 void* stream);
+/* rho_dev[2*q + {0,1}] = (sum cos q.r, -sum sin q.r) as doubles; q_dev: float[3*nq] */
+int hx_density_modes(const hx_float4* position_hi_dev, size_t nparticle, const float* q_dev,
+                     unsigned nq, double* rho_dev, void* stream);
+/* thermodynamic sums over particles i < n, as doubles:
+ * out[0]=sum m v^2, out[1..3]=sum m v, out[4]=sum m, out[5]=sum en_pot, out[6]=sum virial trace
+ * (halmd/observables/gpu/thermodynamics_kernel.cu:35-97).  en_pot/stress may be NULL. */
+int hx_thermodynamics(const hx_float4* velocity_hi_dev, const float* en_pot_dev,
+                      const float* stress_dev, size_t stress_stride, size_t nparticle,
+                      double* out_dev /*8*/, void* stream);
+
+/* ---- step-loop support (device-resident rebuild decision) ------------------------------------
+ * The reference copies 64 floats to the host every step to decide whether the neighbour lists
+ * must be rebuilt (max_displacement.cpp:77-106).  Here the decision stays on the device: a
+ * 4-word control block
+ *   ctl[0] max squared displacement since the last rebuild (float bits, atomicMax),
+ *   ctl[1] halted flag, ctl[2] steps completed in this chunk, ctl[3] reserved
+ * lets the host enqueue a chunk of steps speculatively.  The guarded force kernel evaluates
+ * float(sqrt(ctl[0])) > skin/2 (from_binning.cpp:130-131); when it trips it sets ctl[1] and all
+ * remaining guarded kernels of the chunk return immediately.  The host then rebuilds the lists,
+ * completes the interrupted step and enqueues the next chunk ("chunked stepping"). */
+int hx_ctl_reset(uint32_t* ctl_dev, void* stream);
+int hx_pair_force_guarded(const hx_lj_params* potential, const hx_float4* position1_hi_dev,
+                          const hx_float4* position2_hi_dev, const uint32_t* g_neighbour_dev,
+                          unsigned size, size_t stride, int layout, size_t nparticle,
+                          const float box_length[3], int force_zero, float aux_weight,
+                          hx_float4* force_dev, float* en_pot_dev, float* stress_dev,
+                          size_t stress_stride, uint32_t* ctl_dev, float skin_half, void* stream);
+int hx_andersen_finalize_guarded(hx_float4* velocity_dev, const hx_float4* force_dev,
+                                 size_t nparticle, size_t array_size, float timestep,
+                                 float sqrt_temperature, float coll_prob, const hx_rand48* rng,
+                                 uint16_t* state_dev, const uint32_t* ctl_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HALMD_B200_H */

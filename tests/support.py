@@ -1,0 +1,184 @@
+"""Test support: ctypes access to the CPU oracle (oracle/_build/liboracle.so), to the reference's own
+header-only numerics (oracle/_ref/libhalmd_ref.so, optional) and synthetic input generators.
+
+The oracle is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs use it.
+"""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libhalmd_ref.so")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+PH = 0xFFFFFFFF
+MAXPT = 16
+
+
+def build_oracle():
+    """Compile the C oracle (and oracle/_ref when /root/reference is present)."""
+    subprocess.run(["make", "-C", ORACLE_DIR, "--no-print-directory"], check=True, capture_output=True)
+
+
+def load_oracle():
+    if not os.path.exists(ORACLE_SO):
+        build_oracle()
+    lib = C.CDLL(ORACLE_SO)
+    lib.oracle_array_size.restype = C.c_size_t
+    lib.oracle_array_size.argtypes = [C.c_size_t]
+    lib.oracle_nlist_size.restype = C.c_uint
+    lib.oracle_nlist_size.argtypes = [C.c_float, C.c_float, C.c_size_t, C.c_double, C.c_double, C.c_uint]
+    lib.oracle_hilbert_depth.restype = C.c_uint
+    lib.oracle_hilbert_map_unit.restype = C.c_uint32
+    lib.oracle_hilbert_map_unit.argtypes = [C.c_float, C.c_float, C.c_float, C.c_uint]
+    lib.oracle_displacement_max.restype = C.c_float
+    lib.oracle_binning_update.restype = C.c_int
+    lib.oracle_nlist_build.restype = C.c_int
+    lib.oracle_pair_f.restype = C.c_int
+    lib.oracle_pair_f.argtypes = [C.c_void_p, C.c_uint, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.oracle_pair_d.argtypes = [C.c_double] * 3 + [C.c_int, C.c_double, C.c_double,
+                                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.host_sim_create.restype = C.c_void_p
+    lib.host_sim_rebuilds.restype = C.c_size_t
+    lib.host_sim_pairs.restype = C.c_size_t
+    lib.host_sim_threads.restype = C.c_int
+    return lib
+
+
+def load_ref():
+    """Reference header shim, or None when it was not built (no /root/reference at build time)."""
+    if not os.path.exists(REF_SO):
+        return None
+    lib = C.CDLL(REF_SO)
+    lib.ref_hilbert_map.restype = C.c_uint
+    lib.ref_hilbert_map.argtypes = [C.c_float, C.c_float, C.c_float, C.c_uint]
+    return lib
+
+
+class OLjParams(C.Structure):
+    _fields_ = [
+        ("ntype1", C.c_uint), ("ntype2", C.c_uint), ("truncation", C.c_int), ("rri_smooth", C.c_float),
+        ("epsilon", C.c_float * MAXPT), ("sigma2", C.c_float * MAXPT), ("r_cut", C.c_float * MAXPT),
+        ("rr_cut", C.c_float * MAXPT), ("en_cut", C.c_float * MAXPT),
+    ]
+
+
+class ORand48(C.Structure):
+    _fields_ = [("blocks", C.c_uint), ("threads", C.c_uint), ("a", C.c_uint16 * 3), ("c", C.c_uint16 * 3)]
+
+
+def ptr(a):
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+def d3(v):
+    return (C.c_double * 3)(*[float(x) for x in v])
+
+
+def u3(v):
+    return (C.c_uint * 3)(*[int(x) for x in v])
+
+
+def farr(v):
+    v = [float(x) for x in np.asarray(v).ravel()]
+    return (C.c_float * len(v))(*v)
+
+
+def darr(v):
+    v = [float(x) for x in np.asarray(v).ravel()]
+    return (C.c_double * len(v))(*v)
+
+
+def golden(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+# ---- synthetic inputs ------------------------------------------------------------------------------
+
+def array_size(n):
+    return ((n + 1023) // 1024 if n > 0 else 1) * 1024
+
+
+def fcc_positions(n, L):
+    """fcc lattice filling the box (halmd/mdsim/gpu/positions/lattice.cpp:116-177,
+    halmd/mdsim/positions/lattice_primitive.hpp:121-129), centred on the origin."""
+    L = np.asarray(L, dtype=np.float64)
+    u = 4
+    a = (np.prod(L) / np.ceil(n / u)) ** (1.0 / 3)
+    ncell = np.floor(L / a).astype(np.int64)
+    while n > u * np.prod(ncell):
+        t = L / (ncell + 1)
+        a = t.max()
+        m = ncell.copy()
+        ncell = np.maximum(m, np.floor(L / a).astype(np.int64))
+        if np.all(m == ncell):
+            ncell += 1
+    N = int(u * np.prod(ncell))
+    skip = int(np.ceil(N / (N - n))) if N > n else 0
+    idx = np.arange(N, dtype=np.int64)
+    if skip:
+        keep = np.ones(N, dtype=bool)
+        keep[skip - 1::skip] = False
+        idx = idx[keep][:n]
+    idx = idx[:n]
+    cell = idx >> 2
+    cx = cell % ncell[0]
+    cy = (cell // ncell[0]) % ncell[1]
+    cz = cell // (ncell[0] * ncell[1])
+    r = np.empty((n, 3), dtype=np.float64)
+    r[:, 0] = cx + (((idx ^ (idx >> 1)) & 1) * 2 + 1) / 4.0
+    r[:, 1] = cy + ((idx & 1) * 2 + 1) / 4.0
+    r[:, 2] = cz + ((idx & 2) + 1) / 4.0
+    r *= a
+    r += (L - ncell * a) / 2      # centre the lattice in the box
+    r -= L / 2                    # box spans (-L/2, L/2)
+    return r
+
+
+def melt_like_positions(n, L, rng, jitter=0.12):
+    """fcc lattice + Gaussian displacement, wrapped into (-L/2, L/2): a cheap stand-in for a melted fluid with
+    no overlapping particles (used where the test does not integrate)."""
+    L = np.asarray(L, dtype=np.float64)
+    r = fcc_positions(n, L) + rng.normal(scale=jitter, size=(n, 3))
+    r -= np.rint(r / L) * L
+    return r
+
+
+def pack_state(pos, species=None, vel=None, mass=None):
+    """float4 arrays in HALMD's packing: position/velocity (2A,4) hi then lo planes; ghosts species -1."""
+    n = pos.shape[0]
+    A = array_size(n)
+    p = np.zeros((2 * A, 4), dtype=np.float32)
+    v = np.zeros((2 * A, 4), dtype=np.float32)
+    hi = pos.astype(np.float32)
+    lo = (pos - hi.astype(np.float64)).astype(np.float32)
+    p[:n, :3] = hi
+    p[A:A + n, :3] = lo
+    sp = np.zeros(A, dtype=np.uint32)
+    if species is not None:
+        sp[:n] = species
+    sp[n:] = PH
+    p[:A, 3] = sp.view(np.float32)
+    if vel is not None:
+        vh = vel.astype(np.float32)
+        v[:n, :3] = vh
+        v[A:A + n, :3] = (vel - vh.astype(np.float64)).astype(np.float32)
+    v[:A, 3] = 1.0
+    if mass is not None:
+        v[:n, 3] = mass
+    return p, v, A
+
+
+def species_of(p, A):
+    return p[:A, 3].view(np.uint32)

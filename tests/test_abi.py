@@ -1,0 +1,74 @@
+"""The C-ABI library loads and exports every symbol include/*.h declares (no compute calls: no GPU here)."""
+import ctypes as C
+import glob
+import os
+import re
+
+import numpy as np
+
+import support
+
+
+def declared_symbols():
+    names = set()
+    for h in glob.glob(os.path.join(support.ROOT, "include", "*.h")):
+        text = open(h).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(hxm?_[a-z0-9_]+)\s*\(", text))
+    return names
+
+
+def test_library_exports_all_declared_symbols(hx):
+    names = declared_symbols()
+    assert len(names) >= 38
+    missing = [n for n in sorted(names) if not hasattr(hx.lib, n)]
+    assert not missing, missing
+
+
+def test_python_binding_covers_header(hx):
+    names = {n for n in declared_symbols() if n.startswith("hx_")}
+    assert names == set(hx.KERNEL_SYMBOLS)
+
+
+def test_version_and_error_string(hx):
+    assert hx.lib.hx_version() >= 100
+    assert isinstance(hx.lib.hx_last_error_string(), bytes)
+
+
+def test_host_side_plans_match_oracle(hx, oracle):
+    """Sizing formulas are host code inside the product library; compare with the oracle's restatement."""
+    for row in support.golden("lj_potential.json")["sizing_table"]["rows"]:
+        L = (row["n"] / row["rho"]) ** (1 / 3)
+        ncell, cl, cs = (C.c_uint * 3)(), (C.c_float * 3)(), C.c_uint()
+        hx.check(hx.lib.hx_binning_plan(hx.d3([L] * 3), row["n"], row["rc"], row["skin"], row["occ_bin"], ncell, cl,
+                                        C.byref(cs)))
+        assert list(ncell) == [row["ncell"]] * 3 and cs.value == row["cell_size"]
+        size = C.c_uint()
+        hx.check(hx.lib.hx_nlist_plan(row["rc"], row["skin"], row["n"], L ** 3, row["occ_list"], cs.value, C.byref(size)))
+        assert size.value == row["list_size"]
+        assert hx.lib.hx_array_size(row["n"]) == row["array_size"]
+        assert hx.lib.hx_hilbert_depth(hx.d3([L] * 3)) == row["depth"]
+        ncell_o, cl_o, cs_o = (C.c_uint * 3)(), (C.c_float * 3)(), C.c_uint()
+        oracle.oracle_binning_plan(support.d3([L] * 3), C.c_size_t(row["n"]), C.c_float(row["rc"]), C.c_float(row["skin"]),
+                                   C.c_double(row["occ_bin"]), ncell_o, cl_o, C.byref(cs_o))
+        assert list(cl) == list(cl_o)
+
+
+def test_potential_tables_match_oracle(hx, oracle):
+    eps, sigma, cut = [1.0, 1.5, 1.5, 0.5], [1.0, 0.8, 0.8, 0.88], [2.5] * 4
+    for trunc, h in ((0, 0.0), (1, 0.0), (2, 0.005)):
+        p = hx.LjParams()
+        hx.check(hx.lib.hx_potential_lj_init(C.byref(p), 2, 2, hx.farr(eps), hx.farr(sigma), trunc, hx.farr(cut), h))
+        q = support.OLjParams()
+        oracle.oracle_lj_init(C.byref(q), 2, 2, support.farr(eps), support.farr(sigma), trunc, support.farr(cut), C.c_float(h))
+        assert bytes(p) == bytes(q)
+
+
+def test_contract_violations_return_error_codes(hx):
+    p = hx.LjParams()
+    assert hx.lib.hx_potential_lj_init(C.byref(p), 5, 5, hx.farr([1] * 25), hx.farr([1] * 25), 2, hx.farr([2.5] * 25), 0.005) < 0
+    assert b"ntype" in hx.lib.hx_last_error_string()
+    assert hx.lib.hx_potential_lj_init(C.byref(p), 1, 1, hx.farr([1]), hx.farr([1]), 7, hx.farr([2.5]), 0.005) < 0
+    assert hx.lib.hx_pair_force_set_lanes(3) < 0
+    assert hx.lib.hx_displacement_exceeds(np.float32(0.0626).view(np.uint32).item(), 0.5) == 1   # sqrt(.0626) > .25
+    assert hx.lib.hx_displacement_exceeds(np.float32(0.0624).view(np.uint32).item(), 0.5) == 0

@@ -1,0 +1,111 @@
+"""Pin the oracle's pair-potential functions against the golden tables held by the reference's own unit tests
+(tests/golden/lj_potential.json; sources cited there)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import support
+
+EPS_D = np.finfo(np.float64).eps
+EPS_F = np.finfo(np.float32).eps
+TRUNC = {"sharp": 0, "shifted": 1, "smooth_r4": 2}
+
+
+def close_fraction(a, b, tol):
+    # BOOST_CHECK_CLOSE_FRACTION: |a-b| <= tol * min(|a|,|b|) (strong check); exact zeros must match
+    if a == 0 or b == 0:
+        return abs(a - b) <= tol
+    return abs(a - b) <= tol * min(abs(a), abs(b))
+
+
+def pair_d(oracle, eps, sigma, cutoff, trunc, h, r):
+    f, e = C.c_double(), C.c_double()
+    oracle.oracle_pair_d(eps, sigma, cutoff, trunc, h, r * r, C.byref(f), C.byref(e))
+    return f.value, e.value
+
+
+@pytest.mark.parametrize("trunc", ["sharp", "shifted", "smooth_r4"])
+def test_lj_tables_host_double(oracle, trunc):
+    """lennard_jones.cpp:275-356 — host functor, tolerance 5 eps_double."""
+    g = support.golden("lj_potential.json")
+    lj = g["lennard_jones"]
+    for pair, par in g["pairs"].items():
+        for r, fval, en in lj[trunc][pair]:
+            cutoff_r = lj["cutoff_sigma"] * par["sigma"]
+            f, e = pair_d(oracle, par["epsilon"], par["sigma"], lj["cutoff_sigma"], TRUNC[trunc], lj["h"], r)
+            if r >= cutoff_r:
+                # the functor is only evaluated inside the cutoff by its callers; tables list 0 there
+                if trunc != "sharp" and fval == 0 and en == 0:
+                    continue
+            assert close_fraction(f, fval, 5 * EPS_D), (trunc, pair, r, f, fval)
+            assert close_fraction(e, en, 5 * EPS_D) or abs(e - en) < 1e-19, (trunc, pair, r, e, en)
+
+
+def test_smooth_r4_near_cutoff_double(oracle):
+    """smooth_r4.cpp:48-142 — tolerance k eps (1 + rc / (rc - r))."""
+    g = support.golden("lj_potential.json")
+    t = g["smooth_r4_near_cutoff"]
+    wca = float(np.float32(2.0 ** (1 / 6.0)))
+    cut = {"aa": 2.5, "ab": 2.0, "bb": wca}
+    k = {"aa": 8, "ab": 8, "bb": 9}
+    for pair, par in g["pairs"].items():
+        rc = cut[pair] * par["sigma"]
+        for r, fval, en in t[pair]:
+            f, e = pair_d(oracle, par["epsilon"], par["sigma"], cut[pair], 2, t["h"], r)
+            tol = k[pair] * EPS_D * (1 + rc / (rc - r))
+            assert close_fraction(f, fval, tol), (pair, r, f, fval)
+            assert close_fraction(e, en, tol), (pair, r, e, en)
+
+
+def make_params(oracle, eps, sigma, cutoff, trunc, h):
+    p = support.OLjParams()
+    n = int(round(len(eps) ** 0.5))
+    oracle.oracle_lj_init(C.byref(p), n, n, support.farr(eps), support.farr(sigma), trunc, support.farr(cutoff),
+                          C.c_float(h))
+    return p
+
+
+@pytest.mark.parametrize("trunc", ["sharp", "shifted", "smooth_r4"])
+def test_lj_tables_gpu_functor_float(oracle, trunc):
+    """The float (GPU-semantics) functor against the same tables: lennard_jones.cpp:392-436 compares the GPU
+    kernel with the host functor at 10 eps_float; smooth_r4 adds 8 eps (1 + rc/(rc-r)) (smooth_r4.cpp:229)."""
+    g = support.golden("lj_potential.json")
+    lj = g["lennard_jones"]
+    eps = [1.0, 0.5, 0.5, 0.25]
+    sigma = [1.0, 2.0, 2.0, 4.0]
+    p = make_params(oracle, eps, sigma, [lj["cutoff_sigma"]] * 4, TRUNC[trunc], lj["h"])
+    idx = {"aa": 0, "ab": 1, "bb": 3}
+    for pair, par in g["pairs"].items():
+        rc = lj["cutoff_sigma"] * par["sigma"]
+        for r, fval, en in lj[trunc][pair]:
+            f, e = C.c_float(), C.c_float()
+            rr = np.float32(r) * np.float32(r)
+            inside = oracle.oracle_pair_f(C.byref(p), idx[pair], C.c_float(rr), C.byref(f), C.byref(e))
+            if not inside:
+                assert r >= rc * (1 - 1e-6)
+                continue
+            tol = 10 * EPS_F
+            if trunc == "smooth_r4":
+                tol += 8 * EPS_F * (1 + rc / (rc - r))
+            # r^2 in float carries 1 ulp; r^-14 amplifies it 7-fold
+            tol += 8 * EPS_F
+            assert abs(f.value - fval) <= tol * max(abs(fval), 1e-30), (trunc, pair, r, f.value, fval)
+            # near the zero of the shifted potential only an absolute bound is meaningful
+            assert abs(e.value - en) <= tol * max(abs(en), abs(en - e.value) * 0 + 4 * par["epsilon"] * (par["sigma"] / r) ** 12,
+                                                   1e-30), (trunc, pair, r, e.value, en)
+
+
+def test_lj_init_tables(oracle):
+    """Derived tables as in lennard_jones.cpp:52-70 / smooth_r4.hpp:55-91, KA mixture parameters."""
+    eps = [1.0, 1.5, 1.5, 0.5]
+    sigma = [1.0, 0.8, 0.8, 0.88]
+    p = make_params(oracle, eps, sigma, [2.5] * 4, 2, 0.005)
+    assert p.rri_smooth == np.float32(0.005 ** -2)
+    for i in range(4):
+        s = np.float32(sigma[i])
+        assert p.sigma2[i] == s * s
+        assert p.r_cut[i] == s * np.float32(2.5)
+        assert p.rr_cut[i] == np.float32(p.r_cut[i]) * np.float32(p.r_cut[i])
+        u = 4 * eps[i] * ((1 / 2.5) ** 12 - (1 / 2.5) ** 6)
+        assert abs(p.en_cut[i] - u) < 1e-6 * abs(u)
