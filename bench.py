@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of the MD step loop (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg1]
+
+A bench "step" is one block of --md-steps MD steps (default 1000) of the workload, through the module API
+(sampler:run).  Workload at N=1: BASELINE config 2 — 3-D LJ fluid, N=256,000, rho=0.8442, T=1.2, r_c=2.5 smooth_r4
+(h=0.005), NVE velocity-Verlet dt=0.001, skin 0.5, Hilbert sort at every neighbour-list update; inputs are synthetic
+(fcc lattice + Maxwell-Boltzmann velocities, melted with the Andersen thermostat before timing).
+
+One JSON line is printed by rank 0 (see the contract in the task statement): value = whole-job particle-steps/s
+with the state resident in HBM; e2e = same metric through the public API with host buffers (H2D of positions and
+velocities, D2H of the results inside the timed region); roofline = pair-force kernel vs measured HBM peak;
+cpu_baseline = the host-backend port (oracle/host_backend.c) timed on this box's cores on a bounded sample.
+--impl reference times that CPU port with all host threads as the reference arm.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    "cfg1": dict(kind="lj", n=4000, workload="3D LJ fluid N=4000 rho=0.8442 T=1.2 rc=2.5 smooth_r4 NVE dt=0.001"),
+    "cfg2": dict(kind="lj", n=256000, workload="3D LJ fluid N=256000 rho=0.8442 T=1.2 rc=2.5 smooth_r4 h=0.005 NVE dt=0.001, "
+                                               "skin 0.5, Hilbert sort at every neighbour-list update"),
+    "cfg3": dict(kind="ka", n=1000000, workload="Kob-Andersen 80:20 N=1000000 rho=1.2 T=0.7 rc=2.5sigma smooth_r4, "
+                                                "Andersen NVT rate 2 dt=0.001, skin 0.3 occupancy 0.7"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--md-steps", type=int, default=1000, help="MD steps per bench step")
+    ap.add_argument("--layout", default="row", choices=["row", "column"])
+    ap.add_argument("--lanes", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-steps", type=int, default=40)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.stop_flag, self.index = [], threading.Event(), index
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def start(self):
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag.set()
+        self.thread.join(timeout=6)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        smax = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- CPU legs (the only places allowed to execute oracle/) ----------------------------------------------------------
+def cpu_host_backend(cfg, md_steps, threads, seed=1):
+    """Time the host-backend port (double, half lists, Newton-3) on a bounded sample of the workload."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import support
+    from halmd_b200 import simulation
+    oracle = support.load_oracle()
+    n = cfg["n"]
+    rng = np.random.default_rng(seed)
+    if cfg["kind"] == "lj":
+        rho, T, nt = 0.8442, 1.2, 1
+        eps, sig, skin = [1.0], [1.0], 0.5
+        species = None
+    else:
+        rho, T, nt = 1.2, 0.7, 2
+        eps, sig, skin = [1.0, 1.5, 1.5, 0.5], [1.0, 0.8, 0.8, 0.88], 0.3
+        species = np.ascontiguousarray((np.arange(n) >= int(0.8 * n)).astype(np.uint32))
+    L = (n / rho) ** (1 / 3)
+    pos = np.ascontiguousarray(simulation.fcc_positions(n, [L] * 3))
+    vel = np.ascontiguousarray(simulation.boltzmann_velocities(n, T, rng))
+    sim = oracle.host_sim_create(C.c_size_t(n), support.d3([L] * 3), nt, support.darr(eps), support.darr(sig),
+                                 support.darr([2.5] * (nt * nt)), 2, C.c_double(0.005), C.c_double(skin), C.c_double(0.001), threads)
+    if not sim:
+        raise RuntimeError("host_sim_create failed")
+    sim = C.c_void_p(sim)
+    oracle.host_sim_set(sim, support.ptr(pos), support.ptr(vel), support.ptr(species) if species is not None else None, None)
+    oracle.host_sim_run(sim, C.c_size_t(2))          # builds cells + lists, first forces (untimed)
+    t0 = time.perf_counter()
+    oracle.host_sim_run(sim, C.c_size_t(md_steps))
+    dt = time.perf_counter() - t0
+    used = oracle.host_sim_threads(sim)
+    rebuilds = oracle.host_sim_rebuilds(sim)
+    oracle.host_sim_destroy(sim)
+    return n * md_steps / dt, dt, used, rebuilds
+
+
+def run_reference(args, cfg):
+    """Reference arm: the reference's CPU (host backend) implementation of the path — its port, since the host
+    backend itself cannot be built here (Boost/Lua/HDF5 absent) — with all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = args.cpu_sample_steps
+    vals, times = [], []
+    for i in range(args.warmup + args.steps):
+        v, dt, used, _ = cpu_host_backend(cfg, sample, threads, seed=1 + i)
+        if i >= args.warmup:
+            vals.append(v)
+            times.append(dt)
+    value = cfg["n"] * sample * len(times) / sum(times)
+    line = {
+        "impl": "reference", "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "sample": f"{sample} MD steps of the full N={cfg['n']} system per bench step "
+                   "(host backend port, OpenMP over particles = our parallelisation; the reference host backend is single-threaded)"},
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": used, "kind": "port",
+                         "sample": f"N={cfg['n']}, {sample} MD steps x {args.steps}"},
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- our arm ----------------------------------------------------------------------------------------------------------------
+def build_system(args, cfg, seed):
+    from halmd_b200 import mdsim, simulation
+    if cfg["kind"] == "lj":
+        # melt the lattice with the Andersen thermostat (examples/benchmarks/*/generate_configuration.lua), then NVE
+        s = simulation.lennard_jones_fluid(cfg["n"], seed=seed, layout=args.layout, integrator="andersen", timestep=0.005, rate=2.0)
+        s.run(2000)
+        integ = mdsim.integrators.verlet(box=s.box, particle=s.particle, timestep=0.001)
+        s.integrator, s.core = integ, mdsim.core.get()
+        return s
+    s = simulation.kob_andersen_mixture(cfg["n"], seed=seed, layout=args.layout)
+    s.integrator.set_timestep(0.005)
+    s.run(2000)
+    s.integrator.set_timestep(0.001)
+    return s
+
+
+def force_kernel_roofline(s, args, torch, iters=20):
+    """Average duration of the pair-force kernel, timed alone with CUDA events on its stream, L2 flushed between
+    launches; algorithmic bytes = N * (32 + 4 * mean list length)."""
+    from halmd_b200 import _lib as hx
+    lib = hx.lib
+    p, nb, pot = s.particle, s.neighbour, s.potential
+    n = p.nparticle
+    nb.check()
+    nbar = nb.mean_length()
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+    pos = p.device_ptr("position")
+    force = torch.empty(p.array_size * 4, dtype=torch.float32, device="cuda")
+    L = hx.f3(s.box.length)
+    par = pot.params
+    times = []
+    for i in range(iters + 3):
+        flush.fill_(float(i))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        hx.check(lib.hx_pair_force(C.byref(par), pos, pos, lib.hxm_neighbour_device_ptr(nb._h), nb.size, nb.stride, nb.layout, n,
+                                   L, 1, 0.5, force.data_ptr(), None, None, p.array_size, C.c_void_p(stream.cuda_stream)))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if i >= 3:
+            times.append(e0.elapsed_time(e1) * 1e-3)
+    t = sum(times) / len(times)
+    bytes_alg = n * (32.0 + 4.0 * nbar)
+    peak, how = measured_peaks()
+    achieved = bytes_alg / t / 1e9
+    return {"bound": "hbm", "kernel": "k_force_row" if nb.layout == 1 else "k_force_col", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": how, "avg_launch_us": t * 1e6,
+            "algorithmic_bytes_per_launch": bytes_alg, "mean_list_length": nbar,
+            "pairs_per_s": n * nbar / t, "l2": "flushed between launches (256 MiB write)"}
+
+
+def run_ours(args, cfg):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from halmd_b200 import _lib as hx
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — halmd_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hx.check(hx.lib.hx_pair_force_set_lanes(args.lanes))
+
+    # every rank runs an independent replica of the workload (weak scaling); see DESIGN.md "Multi-GPU"
+    s = build_system(args, cfg, seed=1 + rank)
+    n, md = cfg["n"], args.md_steps
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        s.run(md)
+    barrier()
+    th0 = s.thermodynamics()
+    updates0, launches0 = s.neighbour.updates, hx.lib.hx_launch_count()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        s.run(md)
+    e1.record(stream)
+    barrier()
+    elapsed = e0.elapsed_time(e1) * 1e-3
+    clk = clocks.stop() if rank == 0 else None
+    launches = hx.lib.hx_launch_count() - launches0
+    updates = s.neighbour.updates - updates0
+    th1 = s.thermodynamics()
+    if world > 1:
+        t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+    value = world * n * md * args.steps / elapsed
+
+    # end to end through the public API with host buffers: H2D of the state, block of MD steps, D2H of the results
+    pos_h = s.particle.get("position_ds")
+    vel_h = s.particle.get("velocity_ds")
+    h2d = pos_h.nbytes + vel_h.nbytes
+    d2h = pos_h.nbytes + vel_h.nbytes + 10 * 8
+    e2e_times = []
+    for i in range(2 + min(args.steps, 3)):
+        barrier()
+        t0 = time.perf_counter()
+        s.particle.set("position_ds", pos_h)
+        s.particle.set("velocity_ds", vel_h)
+        s.run(md)
+        pos_h = s.particle.get("position_ds")
+        vel_h = s.particle.get("velocity_ds")
+        th = s.thermodynamics()
+        torch.cuda.synchronize()
+        if i >= 2:
+            e2e_times.append(time.perf_counter() - t0)
+    e2e_t = sum(e2e_times) / len(e2e_times)
+    if world > 1:
+        t = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = float(t.item())
+    e2e_value = world * n * md / e2e_t
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    roof = force_kernel_roofline(s, args, torch)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt, used, _ = cpu_host_backend(cfg, args.cpu_sample_steps, 1)
+        cpu = {"value": v, "unit": "particle-steps/s", "cores": used, "kind": "port",
+               "sample": f"host-backend port (double, half lists), N={n}, {args.cpu_sample_steps} MD steps from the melted-lattice start, {dt:.1f} s"}
+    e_drift = abs(th1["internal_energy"] - th0["internal_energy"]) / abs(th0["internal_energy"])
+    line = {
+        "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 pair math, double-single (2xf32) state, compensated f32 force sums", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "md_steps_per_bench_step": md, "neighbour_layout": args.layout, "lanes_per_particle": args.lanes,
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one per GPU)",
+                   "l2": "working set (neighbour lists + state) exceeds the 126 MB L2; no flush inside the step loop"},
+        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "detail": {"ns_per_particle_step": 1e9 * elapsed / (n * md * args.steps), "list_updates": int(updates),
+                   "md_steps": md * args.steps, "steps_per_update": md * args.steps / max(updates, 1),
+                   "energy_drift_rel": e_drift, "temperature": th1["temperature"], "core": s.core.stats()},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -96,6 +96,69 @@ _protos = {
 
 KERNEL_SYMBOLS = tuple(_protos)
 
+PP = C.POINTER(C.c_void_p)
+U64 = C.c_uint64
+_module_protos = {
+    "hxm_particle_create": (C.c_int, [SZ, C.c_uint, P, PP]),
+    "hxm_particle_destroy": (None, [P]),
+    "hxm_particle_nparticle": (SZ, [P]),
+    "hxm_particle_array_size": (SZ, [P]),
+    "hxm_particle_nspecies": (C.c_uint, [P]),
+    "hxm_particle_set": (C.c_int, [P, C.c_char_p, P]),
+    "hxm_particle_get": (C.c_int, [P, C.c_char_p, P]),
+    "hxm_particle_device_ptr": (P, [P, C.c_char_p]),
+    "hxm_particle_aux_enable": (C.c_int, [P]),
+    "hxm_potential_lj_create": (C.c_int, [C.c_uint, C.c_uint, F3, F3, C.c_int, F3, C.c_float, PP]),
+    "hxm_potential_destroy": (None, [P]),
+    "hxm_potential_r_cut": (C.c_int, [P, F3]),
+    "hxm_potential_params": (C.POINTER(LjParams), [P]),
+    "hxm_binning_create": (C.c_int, [P, D3, F3, C.c_uint, C.c_uint, C.c_double, C.c_double, PP]),
+    "hxm_binning_destroy": (None, [P]),
+    "hxm_binning_ncell": (C.c_int, [P, U3]),
+    "hxm_binning_cell_size": (C.c_uint, [P]),
+    "hxm_binning_update": (C.c_int, [P, P]),
+    "hxm_neighbour_create": (C.c_int, [P, D3, F3, C.c_uint, C.c_uint, C.c_double, C.c_double, C.c_int, C.c_int, P, PP]),
+    "hxm_neighbour_destroy": (None, [P]),
+    "hxm_neighbour_size": (C.c_uint, [P]),
+    "hxm_neighbour_stride": (SZ, [P]),
+    "hxm_neighbour_layout": (C.c_int, [P]),
+    "hxm_neighbour_check": (C.c_int, [P, C.POINTER(C.c_int)]),
+    "hxm_neighbour_updates": (SZ, [P]),
+    "hxm_neighbour_mean_length": (C.c_double, [P]),
+    "hxm_neighbour_get": (C.c_int, [P, P, P]),
+    "hxm_neighbour_device_ptr": (P, [P]),
+    "hxm_force_pair_trunc_create": (C.c_int, [P, P, D3, P, C.c_float, PP]),
+    "hxm_force_destroy": (None, [P]),
+    "hxm_force_apply": (C.c_int, [P]),
+    "hxm_integrator_verlet_create": (C.c_int, [P, P, D3, C.c_double, PP]),
+    "hxm_integrator_andersen_create": (C.c_int, [P, P, D3, C.c_double, C.c_double, C.c_double, C.c_uint, PP]),
+    "hxm_integrator_destroy": (None, [P]),
+    "hxm_integrator_integrate": (C.c_int, [P]),
+    "hxm_integrator_finalize": (C.c_int, [P]),
+    "hxm_integrator_set_timestep": (C.c_int, [P, C.c_double]),
+    "hxm_integrator_set_temperature": (C.c_int, [P, C.c_double]),
+    "hxm_core_create": (C.c_int, [P, PP]),
+    "hxm_core_destroy": (None, [P]),
+    "hxm_core_mdstep": (C.c_int, [P]),
+    "hxm_core_run": (C.c_int, [P, U64]),
+    "hxm_core_step": (U64, [P]),
+    "hxm_core_set_chunk": (C.c_int, [P, C.c_uint, C.c_uint]),
+    "hxm_core_stats": (C.c_int, [P, C.POINTER(U64), C.POINTER(U64), C.POINTER(U64)]),
+    "hxm_core_thermodynamics": (C.c_int, [P, D3]),
+    "hxm_blocking_create": (C.c_int, [P, C.c_double, C.c_double, C.c_uint, C.c_uint, C.c_uint, F3, C.c_uint, U3, C.c_uint, PP]),
+    "hxm_blocking_destroy": (None, [P]),
+    "hxm_blocking_levels": (C.c_uint, [P]),
+    "hxm_blocking_block_size": (C.c_uint, [P]),
+    "hxm_blocking_intervals": (C.c_int, [P, C.POINTER(U64)]),
+    "hxm_blocking_sample": (C.c_int, [P]),
+    "hxm_blocking_finalise": (C.c_int, [P]),
+    "hxm_blocking_msd": (C.c_int, [P, D3]),
+    "hxm_blocking_isf": (C.c_int, [P, D3]),
+    "hxm_core_run_sampling": (C.c_int, [P, U64, P]),
+}
+MODULE_SYMBOLS = tuple(_module_protos)
+_protos.update(_module_protos)
+
 for _name, (_res, _args) in _protos.items():
     _fn = getattr(lib, _name)   # AttributeError here = header/library mismatch: fail loudly
     _fn.restype = _res

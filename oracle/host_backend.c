@@ -302,7 +302,7 @@ void host_sim_force(host_sim* s, int aux)
         int t = omp_get_thread_num();
         double* f = s->tforce + (size_t)t * 3 * n;
         memset(f, 0, 3 * n * sizeof(double));
-#pragma omp for schedule(dynamic, 512)
+#pragma omp for schedule(dynamic, 1)
         for (long b = 0; b < (long)((n + 511) / 512); ++b) {
             size_t lo = (size_t)b * 512, hi = lo + 512 < n ? lo + 512 : n;
             force_range(s, lo, hi, f, NULL, NULL, 0);
