@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--lanes", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-steps", type=int, default=40)
+    ap.add_argument("--melt-steps", type=int, default=2000, help="Andersen steps (dt=0.005) used to melt the lattice before timing")
     return ap.parse_args()
 
 
@@ -167,13 +168,13 @@ def build_system(args, cfg, seed):
     if cfg["kind"] == "lj":
         # melt the lattice with the Andersen thermostat (examples/benchmarks/*/generate_configuration.lua), then NVE
         s = simulation.lennard_jones_fluid(cfg["n"], seed=seed, layout=args.layout, integrator="andersen", timestep=0.005, rate=2.0)
-        s.run(2000)
+        s.run(args.melt_steps)
         integ = mdsim.integrators.verlet(box=s.box, particle=s.particle, timestep=0.001)
         s.integrator, s.core = integ, mdsim.core.get()
         return s
     s = simulation.kob_andersen_mixture(cfg["n"], seed=seed, layout=args.layout)
     s.integrator.set_timestep(0.005)
-    s.run(2000)
+    s.run(args.melt_steps)
     s.integrator.set_timestep(0.001)
     return s
 

@@ -100,6 +100,8 @@ class particle(_Handle):
         self.array_size = lib.hxm_particle_array_size(self._h)
 
     def _shape(self, name):
+        if name not in self._arrays:
+            raise HxError(f"particle: unknown array '{name}'")
         dtype, ncomp = self._arrays[name]
         return dtype, (self.nparticle, ncomp) if ncomp else (self.nparticle,)
 

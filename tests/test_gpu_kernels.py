@@ -442,9 +442,19 @@ def test_verlet_bit_exact(hx, oracle, dev):
         oracle.oracle_verlet_finalize(support.ptr(ov), support.ptr(f), C.c_size_t(A), C.c_float(dt))
     hx.check(hx.lib.hx_verlet_finalize(dev.p(d_v2), dev.p(d_f), A, dt, dev.stream))
     gp, gv, gi = dev.down(d_p), dev.down(d_v), dev.down(d_i)
-    assert np.array_equal(gp, op) and np.array_equal(gv, ov) and np.array_equal(gi, oi)
+
+    def same(name, got, exp):
+        # bit patterns (species tags of ghost slots are NaN as floats); +0 and -0 count as equal
+        bad = np.argwhere((got.view(np.uint32) != exp.view(np.uint32)) & ~((got == 0) & (exp == 0)))
+        assert bad.size == 0, (name, len(bad), bad[:4].tolist(), [(got[tuple(b)], exp[tuple(b)]) for b in bad[:4]])
+
+    same("velocity", gv, ov)
+    same("position", gp, op)
+    same("image", gi, oi)
     assert np.abs(gi[:n, :3]).max() >= 1            # the wrap path was exercised
-    assert np.array_equal(dev.down(d_p2), op) and np.array_equal(dev.down(d_v2), ov) and np.array_equal(dev.down(d_i2), oi)
+    same("fused position", dev.down(d_p2), op)
+    same("fused velocity", dev.down(d_v2), ov)
+    same("fused image", dev.down(d_i2), oi)
 
 
 def test_fused_integrate_displacement_and_guard(hx, oracle, dev):
@@ -468,7 +478,7 @@ def test_fused_integrate_displacement_and_guard(hx, oracle, dev):
     d_ctl = dev.up(ctl)
     hx.check(hx.lib.hx_verlet_finalize_integrate(dev.p(d_p), dev.p(d_i), dev.p(d_v), dev.p(d_f), n, A, dt, hx.f3(L), 1,
                                                  dev.p(d_r0), dev.p(d_ctl), dev.stream))
-    assert np.array_equal(dev.down(d_p), p1)
+    assert dev.down(d_p).tobytes() == p1.tobytes()
 
 
 # ---- a13 rand48 + Andersen --------------------------------------------------------------------------------------

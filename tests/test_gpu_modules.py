@@ -1,0 +1,385 @@
+"""Module-level parity and physics tests through the public API (halmd_b200.mdsim / observables), i.e. through the
+C++ host layer and the C ABI.  They read like the reference's integration tests (test/integration/validation) and
+module unit tests."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import support
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api(cuda):
+    import halmd_b200
+    from halmd_b200 import simulation
+    return halmd_b200, simulation
+
+
+def state_bytes(p):
+    return [p.get(k).tobytes() for k in ("position_ds", "velocity_ds", "image", "id", "reverse_id")]
+
+
+def test_chunked_run_equals_single_steps(api):
+    """sampler:run with the device-resident rebuild decision and fused kernels reproduces, bit for bit, the state of
+    the reference call order (integrate, displacement check on the host, rebuild, force, finalize per step)."""
+    _, simulation = api
+    a = simulation.lennard_jones_fluid(4000, seed=5)
+    b = simulation.lennard_jones_fluid(4000, seed=5)
+    steps = 300
+    for _ in range(steps):
+        a.core.mdstep()
+    b.core.set_chunk(2, 64)
+    b.run(steps)
+    assert a.neighbour.updates == b.neighbour.updates and a.neighbour.updates >= 3
+    assert state_bytes(a.particle) == state_bytes(b.particle)
+    # different chunking, same result; also a run split into pieces
+    c = simulation.lennard_jones_fluid(4000, seed=5)
+    c.core.set_chunk(1, 3)
+    c.run(100)
+    c.run(1)
+    c.run(199)
+    assert state_bytes(a.particle) == state_bytes(c.particle)
+    assert a.core.step == b.core.step == c.core.step == steps
+
+
+def test_andersen_chunked_equals_single_steps(api):
+    _, simulation = api
+    a = simulation.lennard_jones_fluid(4000, seed=6, integrator="andersen", timestep=0.005, rate=2.0)
+    b = simulation.lennard_jones_fluid(4000, seed=6, integrator="andersen", timestep=0.005, rate=2.0)
+    for _ in range(120):
+        a.core.mdstep()
+    b.run(120)
+    assert a.neighbour.updates == b.neighbour.updates
+    assert state_bytes(a.particle) == state_bytes(b.particle)
+
+
+def test_hilbert_order_and_ids(api, oracle, hx):
+    """After a list update the particles are in Hilbert order (stable), ids are a permutation and reverse_id is its
+    inverse (particle.cpp:173-218, sorts/hilbert.cpp:71-117)."""
+    _, simulation = api
+    s = simulation.lennard_jones_fluid(32000, seed=7)
+    s.run(50)
+    s.neighbour.check()
+    p = s.particle
+    n = p.nparticle
+    ids, rid = p.get("id"), p.get("reverse_id")
+    assert np.array_equal(np.sort(ids), np.arange(n))
+    assert np.array_equal(rid[ids], np.arange(n))
+    # keys of the positions at the time of the last update are non-decreasing; particles have moved a little since,
+    # so re-run an update at the current positions and check the order right after it
+    pos = p.get("position")
+    fresh = simulation.lennard_jones_fluid(n, seed=7)
+    fresh.particle.set("position", pos)
+    fresh.neighbour.check()
+    pos2 = fresh.particle.get("position")
+    L = fresh.box.length
+    pk, _, A = support.pack_state(pos2.astype(np.float64))
+    keys = np.zeros(A, dtype=np.uint32)
+    depth = oracle.oracle_hilbert_depth(support.d3(L))
+    oracle.oracle_hilbert_keys(support.ptr(pk), C.c_size_t(A), support.f3(L), depth, support.ptr(keys))
+    assert np.all(np.diff(keys[:n].astype(np.int64)) >= 0)
+    # stable: equal keys keep their previous relative order = ascending previous slot = ascending id here
+    fid = fresh.particle.get("id")
+    same = np.diff(keys[:n].astype(np.int64)) == 0
+    assert np.all(np.diff(fid.astype(np.int64))[same] > 0)
+    # permutation equals the oracle's stable sort of the oracle's keys
+    pk0, _, _ = support.pack_state(pos.astype(np.float64))
+    k0 = np.zeros(A, dtype=np.uint32)
+    oracle.oracle_hilbert_keys(support.ptr(pk0), C.c_size_t(A), support.f3(L), depth, support.ptr(k0))
+    kk, vv = k0[:n].copy(), np.arange(n, dtype=np.uint32)
+    oracle.oracle_sort_pairs_stable(support.ptr(kk), support.ptr(vv), C.c_size_t(n))
+    assert np.array_equal(fid, vv)
+
+
+def test_module_neighbour_lists_match_oracle(api, oracle):
+    """neighbour lists built by the module layer (after sorting) equal the oracle's on the same memory order."""
+    _, simulation = api
+    for layout in ("row", "column"):
+        s = simulation.lennard_jones_fluid(4000, seed=8, layout=layout)
+        s.run(37)
+        pos = s.particle.get("position")
+        fresh = simulation.lennard_jones_fluid(4000, seed=8, layout=layout, disable_sorting=True)
+        fresh.particle.set("position", pos)
+        lists, cnt = fresh.neighbour.lists()
+        n, L = 4000, fresh.box.length
+        pk, _, A = support.pack_state(pos.astype(np.float64))
+        ncell = fresh.neighbour_ncell if hasattr(fresh, "neighbour_ncell") else None
+        nc, cl, cs = (C.c_uint * 3)(), (C.c_float * 3)(), C.c_uint()
+        oracle.oracle_binning_plan(support.d3(L), C.c_size_t(n), C.c_float(2.5), C.c_float(0.5), C.c_double(0.5), nc, cl, C.byref(cs))
+        ncells = int(np.prod(list(nc)))
+        g_cell = np.zeros(ncells * cs.value, dtype=np.uint32)
+        ccnt = np.zeros(ncells, dtype=np.uint32)
+        oracle.oracle_binning_update(support.ptr(pk), C.c_size_t(n), cl, nc, cs.value, support.ptr(g_cell), support.ptr(ccnt))
+        size = fresh.neighbour.size
+        assert size == 239
+        rr = np.array([np.float32(9.0)], dtype=np.float32)
+        o_list = np.zeros(n * 256, dtype=np.uint32)
+        o_cnt = np.zeros(n, dtype=np.uint32)
+        oracle.oracle_nlist_build(support.ptr(g_cell), nc, cs.value, support.ptr(pk), C.c_size_t(n), support.farr(rr), 1,
+                                  support.f3(L), support.ptr(o_list), size, C.c_size_t(256), 1, support.ptr(o_cnt))
+        assert np.array_equal(cnt, o_cnt)
+        rows = o_list.reshape(n, 256)
+        for i in range(n):
+            assert np.array_equal(lists[i], rows[i, :o_cnt[i]])
+
+
+def test_thermodynamics_against_host_backend(api, oracle):
+    """E_kin, E_pot, virial, pressure of the module layer vs the double-precision host-backend port on the same
+    configuration (identical positions / velocities)."""
+    _, simulation = api
+    n = 4000
+    s = simulation.lennard_jones_fluid(n, seed=9)
+    s.run(200)
+    th = s.thermodynamics()
+    pos, vel = s.particle.get("position_ds"), s.particle.get("velocity_ds")
+    L = s.box.length
+    sim = C.c_void_p(oracle.host_sim_create(C.c_size_t(n), support.d3(L), 1, support.darr([1.0]), support.darr([1.0]),
+                                            support.darr([2.5]), 2, C.c_double(0.005), C.c_double(0.5), C.c_double(0.001), 1))
+    pos, vel = np.ascontiguousarray(pos), np.ascontiguousarray(vel)
+    oracle.host_sim_set(sim, support.ptr(pos), support.ptr(vel), None, None)
+    out = np.zeros(6)
+    oracle.host_sim_thermodynamics(sim, support.ptr(out))
+    oracle.host_sim_destroy(sim)
+    assert abs(th["kinetic_energy"] - out[0]) < 1e-6 * abs(out[0])
+    assert abs(th["potential_energy"] - out[1]) < 2e-6 * abs(out[1])
+    assert abs(th["virial"] - out[2]) < 5e-5 * max(abs(out[2]), 1.0)
+    assert abs(th["temperature"] - 2 * out[0] / 3) < 1e-6
+    rho = n / np.prod(L)
+    assert abs(th["pressure"] - rho * (2 * out[0] / 3 + out[2] / 3)) < 1e-4
+    assert np.abs(th["center_of_mass_velocity"]).max() < 1e-6
+
+
+def test_trajectory_tracks_host_backend(api, oracle):
+    """Short-time agreement of the single/double-single GPU path with the double host backend from identical initial
+    conditions (chaos amplifies rounding differences exponentially; 200 steps stay well correlated)."""
+    _, simulation = api
+    n = 4000
+    s = simulation.lennard_jones_fluid(n, seed=10)
+    s.run(500)                                     # leave the lattice
+    p = s.particle
+    ids = p.get("id")
+    pos0, vel0 = p.get("position_ds"), p.get("velocity_ds")
+    L = s.box.length
+    sim = C.c_void_p(oracle.host_sim_create(C.c_size_t(n), support.d3(L), 1, support.darr([1.0]), support.darr([1.0]),
+                                            support.darr([2.5]), 2, C.c_double(0.005), C.c_double(0.5), C.c_double(0.001), 1))
+    a, b = np.ascontiguousarray(pos0), np.ascontiguousarray(vel0)
+    oracle.host_sim_set(sim, support.ptr(a), support.ptr(b), None, None)
+    steps = 200
+    s.run(steps)
+    oracle.host_sim_run(sim, C.c_size_t(steps))
+    hpos = np.zeros((n, 3))
+    oracle.host_sim_get(sim, support.ptr(hpos), None, None, None)
+    oracle.host_sim_destroy(sim)
+    ids1 = p.get("id")
+    gpos = p.get("position_ds")
+    # map both to id order
+    g = np.zeros((n, 3)); g[ids1] = gpos
+    h = np.zeros((n, 3)); h[ids] = hpos
+    d = g - h
+    d -= np.rint(d / L) * L
+    assert np.abs(d).max() < 5e-4
+    assert np.sqrt((d ** 2).mean()) < 2e-5
+
+
+def test_energy_conservation_nve(api):
+    """test/integration/validation/thermodynamics.cpp:150-161 — drift gate max|dE|/|E| < 3e-5 + steps * 3e-13 for the
+    smooth cutoff with double-single integration; here 10^5 steps, N = 4000, rho = 0.8442."""
+    _, simulation = api
+    s = simulation.lennard_jones_fluid(4000, seed=11, integrator="andersen", timestep=0.005, rate=2.0)
+    s.run(2000)                                    # melt + thermalise at T = 1.2
+    from halmd_b200 import mdsim
+    mdsim.integrators.verlet(box=s.box, particle=s.particle, timestep=0.001)
+    s.core = mdsim.core.get()
+    e0 = s.core.thermodynamics()["internal_energy"]
+    worst = 0.0
+    steps = 100000
+    for _ in range(20):
+        s.core.run(steps // 20)
+        th = s.core.thermodynamics()
+        worst = max(worst, abs(th["internal_energy"] - e0) / abs(e0))
+    assert worst < 3e-5 + steps * 3e-13, worst
+    assert 1.0 < th["temperature"] < 1.4
+    assert np.abs(th["center_of_mass_velocity"]).max() < 1e-5
+
+
+def test_andersen_thermostat_reaches_temperature(api):
+    """verlet_nvt_andersen.cpp:103-174 (statistical): temperature and v_cm under the thermostat."""
+    _, simulation = api
+    s = simulation.lennard_jones_fluid(32000, seed=12, temperature=0.3, integrator="andersen", timestep=0.002, rate=5.0)
+    s.integrator.set_temperature(1.5)
+    s.run(4000)
+    temps = []
+    for _ in range(10):
+        s.run(100)
+        temps.append(s.thermodynamics()["temperature"])
+    assert abs(np.mean(temps) - 1.5) < 0.03
+
+
+def test_kob_andersen_mixture(api):
+    """BASELINE config 3 (scaled down): binary mixture with Andersen thermostat, then NVE energy conservation."""
+    _, simulation = api
+    s = simulation.kob_andersen_mixture(32000, seed=13)
+    assert s.neighbour.size >= 64
+    s.integrator.set_timestep(0.004)
+    s.run(1500)
+    s.integrator.set_timestep(0.001)
+    s.run(500)
+    th = s.thermodynamics()
+    assert abs(th["temperature"] - 0.7) < 0.05
+    from halmd_b200 import mdsim
+    mdsim.integrators.verlet(box=s.box, particle=s.particle, timestep=0.001)
+    core = mdsim.core.get()
+    e0 = core.thermodynamics()["internal_energy"]
+    core.run(5000)
+    e1 = core.thermodynamics()["internal_energy"]
+    assert abs(e1 - e0) / abs(e0) < 3e-5
+    sp = s.particle.get("species")
+    assert sp.sum() == 32000 - int(0.8 * 32000)
+
+
+def blocking_reference(n_steps, dt, max_lag, resolution, size, shift, separation):
+    """Pure-Python restatement of blocking_scheme.cpp:75-200 (schedule only): returns the list of
+    (level, [sample steps of the block]) correlation events."""
+    max_interval = int(round(max_lag / dt))
+    s = int(round(resolution / dt))
+    interval = []
+    while s <= max_interval:
+        interval.append(s)
+        if shift > 1 and s * shift <= max_interval:
+            interval.append(s * shift)
+        s *= size
+    origin = [0] * len(interval)
+    blocks = [[] for _ in interval]
+    events = []
+
+    def process(i):
+        events.append((i, list(blocks[i])))
+        skip = max((separation + interval[i] - 1) // interval[i], 1)
+        origin[i] += skip * interval[i]
+        del blocks[i][:skip]
+
+    for step in range(n_steps + 1):
+        for i, iv in enumerate(interval):
+            if step >= origin[i] and (step - origin[i]) % iv == 0:
+                blocks[i].append(step)
+                if len(blocks[i]) == size:
+                    process(i)
+    for i in range(len(interval)):
+        while blocks[i]:
+            process(i)
+    return interval, events
+
+
+def test_blocking_scheme_msd_and_isf(api):
+    """Blocking-scheme schedule, MSD and ISF accumulation vs an independent numpy evaluation on positions sampled
+    through the API at the same steps (the reference has no test for these modules)."""
+    halmd_b200, simulation = api
+    from halmd_b200 import observables
+    n = 4000
+    s = simulation.lennard_jones_fluid(n, seed=14)
+    s.run(300)
+    dt, steps = 0.001, 240
+    wv = observables.utility.wavevector(box=s.box, wavenumber=[2 * np.pi / s.box.length[0] * 2, 7.2], tolerance=0.02, max_count=5)
+    bs = observables.dynamics.blocking_scheme(max_lag=0.12, every=4, size=5, separation=3, wavevector=wv)
+    interval, events = blocking_reference(steps, dt, 0.12, 4 * dt, 5, 2, 3)
+    assert bs.interval == interval
+    # sample trajectory step by step through the API to have an independent record
+    core = halmd_b200.mdsim.core.get()
+    step0 = core.step
+    record = {}
+    L = s.box.length
+
+    def snapshot():
+        p = s.particle
+        ids = p.get("id")
+        r = p.get("position").astype(np.float32)
+        img = p.get("image").astype(np.float32)
+        unfolded = np.zeros((n, 3), dtype=np.float32)
+        unfolded[ids] = (img.astype(np.float64) * L.astype(np.float32).astype(np.float64) + r.astype(np.float64)).astype(np.float32)
+        wrapped = np.zeros((n, 3), dtype=np.float32)
+        wrapped[ids] = r
+        return unfolded, wrapped
+
+    due = sorted({st for _, blk in events for st in blk})
+    for k in range(steps + 1):
+        if k in due:
+            record[k] = snapshot()
+            bs.sample()
+        if k < steps:
+            core.run(1)
+    bs.finalise()
+    assert core.step == step0 + steps
+    msd = bs.mean_square_displacement()
+    isf = bs.intermediate_scattering_function()
+    nlev = len(interval)
+    exp_cnt = np.zeros((nlev, 5))
+    exp_sum = np.zeros((nlev, 5))
+    exp_isf = np.zeros((nlev, 5, len(wv.shell)))
+    exp_isf_cnt = np.zeros((nlev, 5, len(wv.shell)))
+    q = wv.value.astype(np.float32)
+    rho = {}
+    for st, (unf, wr) in record.items():
+        qr = wr.astype(np.float64) @ q.astype(np.float64).T
+        rho[st] = np.stack([np.cos(qr).sum(axis=0), -np.sin(qr).sum(axis=0)], axis=1)
+    for lev, blk in events:
+        first = record[blk[0]][0].astype(np.float64)
+        for lag, st in enumerate(blk):
+            d = record[st][0].astype(np.float64) - first
+            exp_cnt[lev, lag] += n
+            exp_sum[lev, lag] += (d ** 2).sum()
+            for si, (a, b) in enumerate(wv.shell):
+                re = (rho[blk[0]][a:b, 0] * rho[st][a:b, 0] + rho[blk[0]][a:b, 1] * rho[st][a:b, 1]) / n
+                exp_isf[lev, lag, si] += re.sum()
+                exp_isf_cnt[lev, lag, si] += b - a
+    assert np.array_equal(msd["count"], exp_cnt)
+    nz = exp_cnt > 0
+    assert np.allclose(msd["mean"][nz], (exp_sum / np.maximum(exp_cnt, 1))[nz], rtol=1e-5, atol=1e-9)
+    assert np.all(msd["mean"][:, 0][exp_cnt[:, 0] > 0] == 0)
+    assert np.array_equal(isf["count"], exp_isf_cnt)
+    nz = exp_isf_cnt > 0
+    assert np.allclose(isf["mean"][nz], (exp_isf / np.maximum(exp_isf_cnt, 1))[nz], rtol=2e-4, atol=2e-4)
+    # F(q, 0) = S(q) > 0 and decays with lag at the structure-factor peak
+    assert np.all(isf["mean"][0, 0] > 0)
+
+
+def test_run_sampling_matches_manual_sampling(api):
+    """sampler:run(steps) with the blocking scheme connected equals sampling by hand at every step."""
+    halmd_b200, simulation = api
+    from halmd_b200 import observables
+    res = []
+    for mode in ("auto", "manual"):
+        s = simulation.lennard_jones_fluid(4000, seed=15)
+        s.run(100)
+        bs = observables.dynamics.blocking_scheme(max_lag=0.2, every=5, size=4, separation=2)
+        core = halmd_b200.mdsim.core.get()
+        if mode == "auto":
+            observables.sampler.run(150, blocking_scheme=bs)
+        else:
+            for k in range(151):
+                bs.sample()
+                if k < 150:
+                    core.run(1)
+        bs.finalise()
+        res.append(bs.mean_square_displacement())
+    assert np.array_equal(res[0]["count"], res[1]["count"])
+    assert np.array_equal(res[0]["mean"], res[1]["mean"])
+
+
+def test_api_errors(api):
+    halmd_b200, simulation = api
+    from halmd_b200 import mdsim, HxError
+    box = mdsim.box(length=[5.0, 5.0, 5.0])
+    p = mdsim.particle(particles=100)
+    pot = mdsim.potentials.pair.lennard_jones().truncate(cutoff=2.5)
+    assert pot.truncation == "shifted"                       # default truncation (truncate.lua.in:289)
+    with pytest.raises(HxError):
+        mdsim.neighbour(particle=p, box=box, r_cut=pot.r_cut)     # fewer than 3 cells per dimension
+    with pytest.raises(HxError):
+        p.get("nonsense")
+    with pytest.raises(HxError):
+        mdsim.forces.pair(box=box, particle=p, potential=mdsim.potentials.pair.lennard_jones())
+    with pytest.raises(ValueError):
+        mdsim.particle(particles=10, dimension=2)
