@@ -193,7 +193,8 @@ def test_energy_conservation_nve(api):
     from halmd_b200 import mdsim
     mdsim.integrators.verlet(box=s.box, particle=s.particle, timestep=0.001)
     s.core = mdsim.core.get()
-    e0 = s.core.thermodynamics()["internal_energy"]
+    th0 = s.core.thermodynamics()
+    e0 = th0["internal_energy"]
     worst = 0.0
     steps = 100000
     for _ in range(20):
@@ -202,7 +203,8 @@ def test_energy_conservation_nve(api):
         worst = max(worst, abs(th["internal_energy"] - e0) / abs(e0))
     assert worst < 3e-5 + steps * 3e-13, worst
     assert 1.0 < th["temperature"] < 1.4
-    assert np.abs(th["center_of_mass_velocity"]).max() < 1e-5
+    # the Andersen melt does not conserve momentum; the NVE run must (verlet.cpp: pairwise forces only)
+    assert np.abs(np.subtract(th["center_of_mass_velocity"], th0["center_of_mass_velocity"])).max() < 1e-5
 
 
 def test_andersen_thermostat_reaches_temperature(api):
