@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--md-steps", type=int, default=1000, help="MD steps per bench step")
     ap.add_argument("--layout", default="row", choices=["row", "column"])
-    ap.add_argument("--lanes", type=int, default=8)
+    ap.add_argument("--lanes", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-steps", type=int, default=40)
     ap.add_argument("--melt-steps", type=int, default=2000, help="Andersen steps (dt=0.005) used to melt the lattice before timing")

@@ -76,6 +76,7 @@ _protos = {
     "hx_pair_force_guarded": (C.c_int, [C.POINTER(LjParams), P, P, P, C.c_uint, SZ, C.c_int, SZ, F3, C.c_int,
                                         C.c_float, P, P, P, SZ, P, C.c_float, P]),
     "hx_pair_force_set_lanes": (C.c_int, [C.c_int]),
+    "hx_pair_force_set_packed": (C.c_int, [C.c_int]),
     "hx_verlet_integrate": (C.c_int, [P, P, P, P, SZ, C.c_float, F3, P]),
     "hx_verlet_finalize": (C.c_int, [P, P, SZ, C.c_float, P]),
     "hx_verlet_finalize_integrate": (C.c_int, [P, P, P, P, SZ, SZ, C.c_float, F3, C.c_int, P, P, P]),

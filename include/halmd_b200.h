@@ -169,6 +169,8 @@ int hx_pair_force(const hx_lj_params* potential, const hx_float4* position1_hi_d
                   size_t stress_stride, void* stream);
 /* tuning knob for the ROW layout: lanes cooperating on one particle (2, 4 or 8) */
 int hx_pair_force_set_lanes(int lanes);
+/* tuning knob: packed f32x2 arithmetic in the ROW kernel (default 1); 0 selects the scalar instruction stream */
+int hx_pair_force_set_packed(int enable);
 
 /* ---- a12: velocity-Verlet in double-single arithmetic -------------------------------------
  * halmd/mdsim/gpu/integrators/verlet.cpp:64-121, verlet_kernel.cu:37-98,

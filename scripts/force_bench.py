@@ -13,7 +13,21 @@ import bench  # noqa: E402
 from halmd_b200 import _lib as hx  # noqa: E402
 
 
-def time_force(s, lanes, flush, iters=20):
+def sorted_lists(s):
+    """Device copy of the row-layout lists with every row sorted by particle index (experiment: gather locality)."""
+    import numpy as np
+    nb, n = s.neighbour, s.particle.nparticle
+    raw = np.zeros(n * nb.stride, dtype=np.uint32)
+    cnt = np.zeros(n, dtype=np.uint32)
+    hx.check(hx.lib.hxm_neighbour_get(nb._h, raw.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)))
+    rows = raw.reshape(n, nb.stride)
+    k = np.arange(nb.stride)[None, :]
+    rows = np.where(k < cnt[:, None], rows, 0xFFFFFFFF).astype(np.uint32)
+    rows.sort(axis=1)
+    return torch.from_numpy(rows.view(np.int32).copy()).cuda()
+
+
+def time_force(s, lanes, flush, iters=20, lists=None):
     lib = hx.lib
     p, nb, pot = s.particle, s.neighbour, s.potential
     hx.check(lib.hx_pair_force_set_lanes(lanes))
@@ -30,7 +44,7 @@ def time_force(s, lanes, flush, iters=20):
             fl.fill_(float(i))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        hx.check(lib.hx_pair_force(C.byref(par), pos, pos, lib.hxm_neighbour_device_ptr(nb._h), nb.size, nb.stride, nb.layout, n,
+        hx.check(lib.hx_pair_force(C.byref(par), pos, pos, (lists.data_ptr() if lists is not None else lib.hxm_neighbour_device_ptr(nb._h)), nb.size, nb.stride, nb.layout, n,
                                    L, 1, 0.5, force.data_ptr(), None, None, p.array_size, C.c_void_p(stream.cuda_stream)))
         e1.record(stream)
         torch.cuda.synchronize()
@@ -42,6 +56,7 @@ def time_force(s, lanes, flush, iters=20):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--sorted", action="store_true", help="also time the row kernel on index-sorted rows")
     a = ap.parse_args()
     cfg = bench.CONFIGS[a.config]
     out = []
@@ -52,11 +67,19 @@ def main():
         s.neighbour.check()
         nbar = s.neighbour.mean_length()
         for lanes in ((2, 4, 8) if layout == "row" else (8,)):
+            for packed in ((1, 0) if layout == "row" else ()):
+                hx.check(hx.lib.hx_pair_force_set_packed(packed))
+                avg, best = time_force(s, lanes, True)
+                print(json.dumps(dict(layout=layout, lanes=lanes, packed=packed, avg_us=avg, min_us=best)), flush=True)
+            hx.check(hx.lib.hx_pair_force_set_packed(1))
             for flush in (True, False):
                 avg, best = time_force(s, lanes, flush)
                 out.append(dict(layout=layout, lanes=lanes, flush=flush, avg_us=avg, min_us=best, nbar=nbar,
                                 gbs=cfg["n"] * (32 + 4 * nbar) / avg / 1e3))
                 print(json.dumps(out[-1]), flush=True)
+            if layout == "row" and a.sorted:
+                avg, best = time_force(s, lanes, True, lists=sorted_lists(s))
+                print(json.dumps(dict(layout=layout, lanes=lanes, flush=True, sorted_rows=True, avg_us=avg, min_us=best)), flush=True)
         del s
 
 
