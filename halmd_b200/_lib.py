@@ -93,6 +93,16 @@ _protos = {
     "hx_density_modes": (C.c_int, [P, SZ, P, C.c_uint, P, P]),
     "hx_thermodynamics": (C.c_int, [P, P, P, SZ, SZ, P, P]),
     "hx_ctl_reset": (C.c_int, [P, P]),
+    "hx_nlist_build2": (C.c_int, [P, U3, C.c_uint, P, SZ, SZ, F3, C.c_uint, C.c_uint, F3, P, C.c_uint, SZ,
+                                  C.c_int, C.c_int, P, P, P]),
+    "hx_pair_force2": (C.c_int, [C.POINTER(LjParams), P, P, SZ, P, C.c_uint, SZ, C.c_int, SZ, F3, C.c_int,
+                                 C.c_float, P, P, P, SZ, P, C.c_float, P]),
+    "hx_verlet_finalize_integrate_range": (C.c_int, [P, P, P, P, SZ, SZ, SZ, C.c_float, F3, C.c_int, C.c_int, P, P, P]),
+    "hx_dd_owner_keys": (C.c_int, [P, SZ, C.c_float, C.c_float, C.c_int, C.c_int, P, P, P]),
+    "hx_dd_ghost_keys": (C.c_int, [P, SZ, C.c_float, C.c_float, C.c_float, C.c_int, P, P, P]),
+    "hx_dd_permute": (C.c_int, [P, SZ, SZ, P, P, P, P, P, P, P, P, P]),
+    "hx_gather_float4": (C.c_int, [P, P, SZ, P, P, P]),
+    "hx_gather_u32": (C.c_int, [P, P, SZ, P, P]),
 }
 
 KERNEL_SYMBOLS = tuple(_protos)

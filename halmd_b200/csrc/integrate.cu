@@ -49,13 +49,13 @@ __device__ __forceinline__ float drift_wrap(ds& r, ds v, float dt, float L)
 template <bool FINALIZE, bool INTEGRATE>
 __global__ void __launch_bounds__(128) k_verlet(float4* __restrict__ pos, float4* __restrict__ image,
                                                float4* __restrict__ vel, const float4* __restrict__ force,
-                                               unsigned n, unsigned A, float dt, vec3 L, vec3 invL,
+                                               unsigned n, unsigned nproc, unsigned A, float dt, vec3 L, vec3 invL,
                                                const float4* __restrict__ r0, unsigned* __restrict__ ctl)
 {
     if (ctl && ctl[CTL_HALTED]) return;
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     float rr = 0.f;
-    if (i < A) {
+    if (i < nproc) {
         float4 vh = vel[i], vl = vel[i + A];
         float4 f = force[i];
         float const mass = vh.w;
@@ -252,9 +252,10 @@ int hx_state_init(hx_float4* position_dev, hx_float4* velocity_dev, hx_float4* i
 
 static int verlet_launch(bool fin, bool integ, hx_float4* pos, hx_float4* image, hx_float4* vel,
                          const hx_float4* force, size_t n, size_t A, float dt, const float L[3],
-                         const hx_float4* r0, uint32_t* ctl, void* stream)
+                         const hx_float4* r0, uint32_t* ctl, void* stream, size_t nproc_arg = ~size_t(0))
 {
-    if (!vel || !force || A == 0 || A >= 0x7FFFFFFFull || n > A || (integ && (!pos || !image || !L))
+    size_t const nproc = nproc_arg == ~size_t(0) ? A : nproc_arg;
+    if (!vel || !force || A == 0 || A >= 0x7FFFFFFFull || n > A || nproc > A || (integ && (!pos || !image || !L))
         || (r0 && !ctl)) {
         set_error("hx_verlet: invalid argument");
         return HX_E_INVALID;
@@ -264,17 +265,17 @@ static int verlet_launch(bool fin, bool integ, hx_float4* pos, hx_float4* image,
         Lv = make_vec3(L);
         iLv = {1.0f / L[0], 1.0f / L[1], 1.0f / L[2]};
     }
-    dim3 grid(div_up(A, 128)), block(128);
+    dim3 grid(div_up(nproc > 0 ? nproc : 1, 128)), block(128);
     cudaStream_t st = as_stream(stream);
     float4* p = reinterpret_cast<float4*>(pos);
     float4* im = reinterpret_cast<float4*>(image);
     float4* v = reinterpret_cast<float4*>(vel);
     const float4* f = reinterpret_cast<const float4*>(force);
     const float4* q = reinterpret_cast<const float4*>(r0);
-    unsigned nn = static_cast<unsigned>(n), AA = static_cast<unsigned>(A);
-    if (fin && integ) k_verlet<true, true><<<grid, block, 0, st>>>(p, im, v, f, nn, AA, dt, Lv, iLv, q, ctl);
-    else if (integ) k_verlet<false, true><<<grid, block, 0, st>>>(p, im, v, f, nn, AA, dt, Lv, iLv, q, ctl);
-    else k_verlet<true, false><<<grid, block, 0, st>>>(p, im, v, f, nn, AA, dt, Lv, iLv, q, ctl);
+    unsigned nn = static_cast<unsigned>(n), AA = static_cast<unsigned>(A), np = static_cast<unsigned>(nproc);
+    if (fin && integ) k_verlet<true, true><<<grid, block, 0, st>>>(p, im, v, f, nn, np, AA, dt, Lv, iLv, q, ctl);
+    else if (integ) k_verlet<false, true><<<grid, block, 0, st>>>(p, im, v, f, nn, np, AA, dt, Lv, iLv, q, ctl);
+    else k_verlet<true, false><<<grid, block, 0, st>>>(p, im, v, f, nn, np, AA, dt, Lv, iLv, q, ctl);
     return check_launch("k_verlet");
 }
 
@@ -300,6 +301,16 @@ int hx_verlet_finalize_integrate(hx_float4* position_dev, hx_float4* image_dev, 
 {
     return verlet_launch(do_finalize != 0, true, position_dev, image_dev, velocity_dev, force_dev, nparticle,
                          array_size, timestep, box_length, r0_dev, ctl_dev, stream);
+}
+
+int hx_verlet_finalize_integrate_range(hx_float4* position_dev, hx_float4* image_dev, hx_float4* velocity_dev,
+                                       const hx_float4* force_dev, size_t nparticle, size_t nprocess, size_t array_size,
+                                       float timestep, const float box_length[3], int do_finalize, int do_integrate,
+                                       const hx_float4* r0_dev, uint32_t* ctl_dev, void* stream)
+{
+    if (!do_finalize && !do_integrate) return HX_OK;
+    return verlet_launch(do_finalize != 0, do_integrate != 0, position_dev, image_dev, velocity_dev, force_dev, nparticle,
+                         array_size, timestep, box_length, do_integrate ? r0_dev : nullptr, ctl_dev, stream, nprocess);
 }
 
 int hx_verlet_finalize_guarded(hx_float4* velocity_dev, const hx_float4* force_dev, size_t array_size,

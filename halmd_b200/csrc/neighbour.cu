@@ -21,6 +21,7 @@ struct nlist_args {
     uvec3 ncell;
     unsigned cell_size;
     unsigned size;
+    unsigned nbuild;           // lists are built for particles with index < nbuild (all others are partners only)
     size_t stride;
     vec3 L, invL;
     unsigned ntype2;
@@ -64,7 +65,8 @@ __global__ void __launch_bounds__(NL_THREADS) k_nlist_build(nlist_args a)
     unsigned const cs = a.cell_size;
 
     // occupied entries sit at the front of each cell (ascending index, placeholders last)
-    if (a.g_cell[static_cast<size_t>(cell) * cs] == HX_PH) return;   // empty home cell
+    // empty home cell, or one that holds partners only (their indices follow those of the list owners)
+    if (a.g_cell[static_cast<size_t>(cell) * cs] >= a.nbuild) return;
 
     int const cx = cell % a.ncell.x;
     int const cy = (cell / a.ncell.x) % a.ncell.y;
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(NL_THREADS) k_nlist_build(nlist_args a)
 
     for (unsigned p = warp; p < home_cnt; p += NL_WARPS) {
         unsigned const n = s_id[home_off + p];
+        if (n >= a.nbuild) break;                  // ascending indices within a cell: the rest are partners only
         float4 const r1 = s_pos[home_off + p];
         unsigned const type1 = __float_as_uint(r1.w);
         unsigned* row = ROW ? a.g_neighbour + static_cast<size_t>(n) * a.stride : a.g_neighbour + n;
@@ -161,11 +164,11 @@ __global__ void __launch_bounds__(NL_THREADS) k_nlist_build(nlist_args a)
 
 using namespace hx;
 
-extern "C" int hx_nlist_build(const uint32_t* g_cell_dev, const unsigned ncell[3], unsigned cell_size,
-                              const hx_float4* position_hi_dev, size_t nparticle, const float* rr_cut_skin,
-                              unsigned ntype1, unsigned ntype2, const float box_length[3],
-                              uint32_t* g_neighbour_dev, unsigned size, size_t stride, int layout,
-                              int fill_all, uint32_t* count_dev, int* overflow_flag_dev, void* stream)
+static int nlist_build_impl(const uint32_t* g_cell_dev, const unsigned ncell[3], unsigned cell_size,
+                            const hx_float4* position_hi_dev, size_t nparticle, size_t nbuild, const float* rr_cut_skin,
+                            unsigned ntype1, unsigned ntype2, const float box_length[3],
+                            uint32_t* g_neighbour_dev, unsigned size, size_t stride, int layout,
+                            int fill_all, uint32_t* count_dev, int* overflow_flag_dev, void* stream)
 {
     if (!g_cell_dev || !ncell || !position_hi_dev || !rr_cut_skin || !box_length || !g_neighbour_dev
         || !overflow_flag_dev || size == 0 || cell_size == 0 || cell_size % 32 != 0
@@ -184,7 +187,7 @@ extern "C" int hx_nlist_build(const uint32_t* g_cell_dev, const unsigned ncell[3
             return HX_E_INVALID;
         }
     } else if (layout == HX_LAYOUT_COLUMN) {
-        if (stride < nparticle) {
+        if (stride < (nbuild < nparticle ? nbuild : nparticle)) {
             set_error("hx_nlist_build: column stride must be >= nparticle");
             return HX_E_INVALID;
         }
@@ -208,6 +211,7 @@ extern "C" int hx_nlist_build(const uint32_t* g_cell_dev, const unsigned ncell[3
     a.ncell = {ncell[0], ncell[1], ncell[2]};
     a.cell_size = cell_size;
     a.size = size;
+    a.nbuild = static_cast<unsigned>(nbuild < nparticle ? nbuild : nparticle);
     a.stride = stride;
     a.L = make_vec3(box_length);
     a.invL = {1.0f / box_length[0], 1.0f / box_length[1], 1.0f / box_length[2]};
@@ -238,4 +242,24 @@ extern "C" int hx_nlist_build(const uint32_t* g_cell_dev, const unsigned ncell[3
         k_nlist_build<true><<<static_cast<unsigned>(ncells), NL_THREADS, smem, st>>>(a);
     }
     return check_launch("k_nlist_build");
+}
+
+extern "C" int hx_nlist_build(const uint32_t* g_cell_dev, const unsigned ncell[3], unsigned cell_size,
+                              const hx_float4* position_hi_dev, size_t nparticle, const float* rr_cut_skin,
+                              unsigned ntype1, unsigned ntype2, const float box_length[3],
+                              uint32_t* g_neighbour_dev, unsigned size, size_t stride, int layout,
+                              int fill_all, uint32_t* count_dev, int* overflow_flag_dev, void* stream)
+{
+    return nlist_build_impl(g_cell_dev, ncell, cell_size, position_hi_dev, nparticle, nparticle, rr_cut_skin, ntype1, ntype2,
+                            box_length, g_neighbour_dev, size, stride, layout, fill_all, count_dev, overflow_flag_dev, stream);
+}
+
+extern "C" int hx_nlist_build2(const uint32_t* g_cell_dev, const unsigned ncell[3], unsigned cell_size,
+                               const hx_float4* position_hi_dev, size_t nparticle, size_t nbuild,
+                               const float* rr_cut_skin, unsigned ntype1, unsigned ntype2, const float box_length[3],
+                               uint32_t* g_neighbour_dev, unsigned size, size_t stride, int layout, int fill_all,
+                               uint32_t* count_dev, int* overflow_flag_dev, void* stream)
+{
+    return nlist_build_impl(g_cell_dev, ncell, cell_size, position_hi_dev, nparticle, nbuild, rr_cut_skin, ntype1, ntype2,
+                            box_length, g_neighbour_dev, size, stride, layout, fill_all, count_dev, overflow_flag_dev, stream);
 }

@@ -1,0 +1,616 @@
+"""Slab domain decomposition of the MD step loop across the GPUs of one node (one process per GPU).
+
+The reference has no multi-GPU mode (doc/usage/multi-gpu.rst.in runs independent replicas); this module is new
+(SURVEY §8e).  Rank r of P owns the particles whose wrapped x coordinate lies in
+[-L_x/2 + r*W, -L_x/2 + (r+1)*W), W = L_x / P, and keeps ghost copies of the particles of its two neighbours that lie
+within r_c + skin of its faces.  Particle coordinates stay global, so the kernels' minimum-image convention handles
+the periodic wrap, and binning uses the *global* cell grid of the single-GPU run: every owned particle therefore gets
+exactly the neighbour set the single-GPU code would give it.
+
+Per MD step:   fused finalize/integrate (owned) -> pack + exchange ghost positions -> all-reduce(max) of the
+               displacement word -> guarded pair force (owned rows, ghost partners)
+Per list update (when the device-side displacement test trips): migrate leavers to the neighbouring ranks, Hilbert
+order, select + exchange ghosts, bin, build lists, reset displacement origin.
+
+Three layers, so that the host logic is testable without a GPU:
+  SlabDecomposition  geometry and ownership arithmetic (pure numpy restatement of csrc/dd.cu, used by the tests)
+  Exchange           neighbour exchange / reductions over torch.distributed (NCCL on device tensors; gloo stages
+                     through host memory, which is what the CPU tests and the single-GPU two-rank test use)
+  DecomposedSystem   device state + step loop through the C ABI (needs CUDA; no CPU fallback)
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+__all__ = ["SlabDecomposition", "Exchange", "DecomposedSystem"]
+
+
+class SlabDecomposition:
+    """Geometry of the slab decomposition along x; float32 arithmetic identical to csrc/dd.cu."""
+
+    def __init__(self, box_length, nranks, rank, halo):
+        self.L = np.asarray(box_length, dtype=np.float64)
+        self.nranks, self.rank = int(nranks), int(rank)
+        if not (0 <= self.rank < self.nranks):
+            raise ValueError("rank out of range")
+        self.x0 = np.float32(-self.L[0] / 2)
+        self.width = np.float32(self.L[0] / self.nranks)
+        self.inv_width = np.float32(1.0) / self.width
+        # a little slack absorbs the rounding differences between slab_of() and the face coordinates
+        self.halo = np.float32(float(halo) * (1 + 1e-5) + 1e-4)
+        self.lo = np.float32(self.x0 + np.float32(self.rank) * self.width)
+        self.hi = np.float32(self.lo + self.width)
+        self.left = (self.rank - 1) % self.nranks
+        self.right = (self.rank + 1) % self.nranks
+        if self.nranks > 1:
+            if self.nranks == 2:
+                if self.L[0] / 2 < float(self.halo):
+                    raise ValueError("box too small for two slabs: L_x / 2 < r_c + skin")
+            elif float(self.width) < float(self.halo):
+                raise ValueError("slab width below r_c + skin: use fewer ranks")
+
+    def slab_of(self, x):
+        """Owner slab of wrapped coordinates x (float32), as k_dd_owner_keys computes it."""
+        x = np.asarray(x, dtype=np.float32)
+        s = np.floor((x - self.x0) * self.inv_width).astype(np.int64)
+        return np.mod(s, self.nranks)
+
+    def owner_keys(self, x):
+        """0 stays, 1 to the left neighbour, 2 to the right neighbour (1 for both when P = 2), 3 lost."""
+        s = self.slab_of(x)
+        key = np.full(s.shape, 3, dtype=np.uint32)
+        key[s == self.right] = 2
+        key[s == self.left] = 1
+        key[s == self.rank] = 0
+        if self.nranks == 2:
+            key[key == 2] = 1
+        return key
+
+    def ghost_mask(self, x, side):
+        """Particles within the halo of the low (0), high (1) or either (2) face."""
+        x = np.asarray(x, dtype=np.float32)
+        near_lo = (x - self.lo) < self.halo
+        near_hi = (self.hi - x) < self.halo
+        return near_lo if side == 0 else (near_hi if side == 1 else (near_lo | near_hi))
+
+    def ghost_sides(self):
+        """Ghost messages of a list update as (side, destination): one combined list for two ranks (both faces
+        border the same peer, which must receive every particle once), low/high lists otherwise."""
+        if self.nranks == 1:
+            return []
+        if self.nranks == 2:
+            return [(2, "left")]
+        return [(0, "left"), (1, "right")]
+
+
+class Exchange:
+    """Neighbour exchange along the slab direction and small reductions, on torch.distributed.
+
+    A "leftward" message travels to rank-1 and is received from rank+1; a "rightward" one the other way round.  With
+    two ranks both directions connect the same pair, so operations are always issued leftward first (NCCL matches
+    point-to-point operations per peer in issue order; gloo additionally gets distinct tags)."""
+
+    def __init__(self, rank=0, nranks=1, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.nranks, self.group = rank, nranks, group
+        self.left, self.right = (rank - 1) % nranks, (rank + 1) % nranks
+        self.backend = dist.get_backend(group) if (nranks > 1 and dist.is_initialized()) else None
+        self.stage = self.backend == "gloo"        # gloo moves host memory: device tensors are staged
+        self.bytes_sent = 0
+
+    def _wire(self, t):
+        return t.cpu() if (self.stage and t.is_cuda) else t
+
+    def sendrecv(self, leftward=None, rightward=None, from_right=None, from_left=None):
+        """Send `leftward` to rank-1 and `rightward` to rank+1; fill `from_right` with the leftward message of rank+1
+        and `from_left` with the rightward message of rank-1.  Tensors may be None or empty (skipped on both ends:
+        the caller exchanges the sizes first)."""
+        if self.nranks == 1:
+            return
+        dist, ops, post = self.dist, [], []
+
+        def send(t, peer, tag):
+            if t is not None and t.numel() > 0:
+                w = self._wire(t.contiguous())
+                self.bytes_sent += w.numel() * w.element_size()
+                ops.append(dist.P2POp(dist.isend, w, peer, self.group, tag))
+
+        def recv(t, peer, tag):
+            if t is not None and t.numel() > 0:
+                if self.stage and t.is_cuda:
+                    w = self.torch.empty(t.shape, dtype=t.dtype, device="cpu")
+                    post.append((t, w))
+                else:
+                    assert t.is_contiguous()
+                    w = t
+                ops.append(dist.P2POp(dist.irecv, w, peer, self.group, tag))
+
+        send(leftward, self.left, 0)
+        recv(from_right, self.right, 0)
+        send(rightward, self.right, 1)
+        recv(from_left, self.left, 1)
+        if ops:
+            for work in dist.batch_isend_irecv(ops):
+                work.wait()
+        for t, w in post:
+            t.copy_(w)
+
+    def exchange_counts(self, n_leftward, n_rightward):
+        """Sizes of the messages about to arrive: (from_right, from_left)."""
+        if self.nranks == 1:
+            return 0, 0
+        torch = self.torch
+        dev = "cpu" if self.stage else "cuda"
+        a = torch.tensor([n_leftward], dtype=torch.int64, device=dev)
+        b = torch.tensor([n_rightward], dtype=torch.int64, device=dev)
+        ra, rb = torch.zeros_like(a), torch.zeros_like(b)
+        self.sendrecv(a, b, ra, rb)
+        return int(ra.item()), int(rb.item())
+
+    def allreduce(self, t, op="sum"):
+        if self.nranks == 1:
+            return t
+        dist = self.dist
+        o = {"sum": dist.ReduceOp.SUM, "max": dist.ReduceOp.MAX}[op]
+        if self.stage and t.is_cuda:
+            w = t.cpu()
+            dist.all_reduce(w, op=o, group=self.group)
+            t.copy_(w)
+        else:
+            dist.all_reduce(t, op=o, group=self.group)
+        return t
+
+    def barrier(self):
+        if self.nranks > 1:
+            self.dist.barrier(group=self.group)
+
+
+def _round_up(n, m):
+    return ((int(n) + m - 1) // m) * m
+
+
+class DecomposedSystem:
+    """One rank's share of a slab-decomposed LJ system: device state, neighbour structures and the step loop.
+
+    Arrays have `cap` slots: owned particles in [0, n_own), ghosts in [n_own, n_own + n_ghost).  All kernels are the
+    single-GPU ones, called through the C ABI with explicit counts (hx_*2 / hx_*_range / hx_dd_*)."""
+
+    def __init__(self, box_length, positions, velocities, ids, species=None, nspecies=1, epsilon=(1.0,), sigma=(1.0,),
+                 cutoff=(2.5,), truncation="smooth_r4", h=0.005, skin=0.5, timestep=0.001, integrator="verlet",
+                 temperature=1.2, rate=2.0, seed=1, n_global=None, rank=0, nranks=1, group=None, occupancy=None,
+                 lanes=4, capacity=None, sorting=True):
+        import torch
+        from . import _lib as hx
+        if not torch.cuda.is_available():
+            raise hx.HxError("DecomposedSystem needs a CUDA device (halmd_b200 has no CPU fallback)")
+        self.torch, self.hx, self.lib = torch, hx, hx.lib
+        self.rank, self.nranks = rank, nranks
+        self.L = np.asarray(box_length, dtype=np.float64)
+        self.Lf = hx.f3(self.L)
+        self.stream = torch.cuda.current_stream()
+        self.st = C.c_void_p(self.stream.cuda_stream)
+        self.dt = float(timestep)
+        self.skin = float(skin)
+        self.skin_half = float(np.float32(np.float32(skin) / 2))
+        self.kind = integrator
+        self.step = 0
+        self.updates = 0
+        self.sorting = sorting
+        self.stats = {"chunks": 0, "syncs": 0, "migrated": 0}
+        hx.check(self.lib.hx_pair_force_set_lanes(lanes))
+
+        nt = int(nspecies)
+        trunc = {"sharp": hx.TRUNC_SHARP, "shifted": hx.TRUNC_SHIFTED, "smooth_r4": hx.TRUNC_SMOOTH_R4}[truncation]
+        self.pot = hx.LjParams()
+        hx.check(self.lib.hx_potential_lj_init(C.byref(self.pot), nt, nt, hx.farr(epsilon), hx.farr(sigma), trunc,
+                                               hx.farr(cutoff), float(h)), "potential")
+        r_cut = np.array([self.pot.r_cut[i] for i in range(nt * nt)], dtype=np.float32)
+        self.nt = nt
+        self.r_cut_max = float(r_cut.max())
+        self.rr_cut_skin = hx.farr(((r_cut + np.float32(skin)).astype(np.float64) ** 2).astype(np.float32))
+        self.dec = SlabDecomposition(self.L, nranks, rank, self.r_cut_max + skin)
+        self.ex = Exchange(rank, nranks, group)
+
+        n_own = int(positions.shape[0])
+        self.n_global = int(n_global if n_global is not None else n_own)
+        # global cell grid and list size: identical to the single-GPU plan (binning.cpp:81-101, from_binning.cpp:96-119)
+        ncell, cl, cs = (C.c_uint * 3)(), (C.c_float * 3)(), C.c_uint()
+        occ_b = float(occupancy) if occupancy else 0.5
+        occ_n = float(occupancy) if occupancy else 0.4
+        hx.check(self.lib.hx_binning_plan(hx.d3(self.L), self.n_global, self.r_cut_max, float(skin), occ_b, ncell, cl, C.byref(cs)))
+        self.ncell, self.cell_length, self.cell_size = ncell, cl, cs.value
+        if min(ncell) < 3:
+            raise hx.HxError("neighbour: number of cells per dimension must be at least 3")
+        self.ncells = int(np.prod(list(ncell)))
+        size = C.c_uint()
+        hx.check(self.lib.hx_nlist_plan(self.r_cut_max, float(skin), self.n_global, float(np.prod(self.L)), occ_n, self.cell_size, C.byref(size)))
+        self.occ_n = occ_n
+        self.size = size.value
+        self.stride = ((self.size + 32) // 32) * 32
+        self.depth = self.lib.hx_hilbert_depth(hx.d3(self.L))
+
+        # capacity: owned share with head room + two ghost layers
+        share = self.n_global / nranks
+        ghost_frac = 0.0 if nranks == 1 else min(1.0, 2.0 * float(self.dec.halo) / float(self.dec.width))
+        if capacity is None:
+            own_cap = _round_up(max(n_own, share) * 1.08 + 4096, 1024)
+            capacity = _round_up(own_cap + share * ghost_frac * 1.15 + 4096, 1024)
+        else:
+            own_cap = _round_up(min(capacity, max(n_own, share) * 1.08 + 4096), 1024)
+        self.cap, self.own_cap = int(capacity), int(own_cap)
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        f32, i32 = torch.float32, torch.int32
+        z = lambda *shape, dtype=f32: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
+        cap = self.cap
+        self.pos, self.pos_b = z(2 * cap, 4), z(2 * cap, 4)
+        self.vel, self.vel_b = z(2 * cap, 4), z(2 * cap, 4)
+        self.image, self.image_b = z(cap, 4), z(cap, 4)
+        self.force = z(cap, 4)
+        self.id, self.id_b = z(cap, dtype=i32), z(cap, dtype=i32)
+        self.en_pot, self.stress = z(cap), z(6 * cap)
+        self.r0 = z(self.own_cap, 4)
+        self.keys, self.index = z(cap, dtype=i32), z(cap, dtype=i32)
+        self.sort_bytes = self.lib.hx_sort_scratch_bytes(cap)
+        self.sort_scratch = torch.empty(self.sort_bytes, dtype=torch.uint8, device=dev)
+        self.counts = z(4, dtype=i32)
+        self.ctl = z(4, dtype=i32)
+        self.flags = z(2, dtype=i32)
+        self.g_cell = torch.empty(self.ncells * self.cell_size, dtype=i32, device=dev)
+        self.cell_count = z(self.ncells, dtype=i32)
+        self.nl = torch.empty(self.own_cap * self.stride, dtype=i32, device=dev)
+        self.nl_count = z(self.own_cap, dtype=i32)
+        self.thermo = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.send_idx = {"left": z(0, dtype=i32), "right": z(0, dtype=i32)}
+        self.send_buf = {"left": z(0, 4), "right": z(0, 4)}
+        self.n_ghost_from = {"left": 0, "right": 0}
+
+        # upload the owned particles (double-single split as dsdeq, dsfun.hpp:122-126)
+        self.n_own, self.n_ghost = n_own, 0
+        if n_own > self.own_cap:
+            raise hx.HxError("initial share exceeds the capacity")
+        pos = np.asarray(positions, dtype=np.float64)
+        vel = np.asarray(velocities, dtype=np.float64)
+        sp = np.zeros(n_own, dtype=np.uint32) if species is None else np.asarray(species, dtype=np.uint32)
+        ph = np.zeros((n_own, 4), dtype=np.float32)
+        pl = np.zeros((n_own, 4), dtype=np.float32)
+        ph[:, :3] = pos
+        pl[:, :3] = pos - ph[:, :3].astype(np.float64)
+        ph[:, 3] = sp.view(np.float32)
+        vh = np.zeros((n_own, 4), dtype=np.float32)
+        vl = np.zeros((n_own, 4), dtype=np.float32)
+        vh[:, :3] = vel
+        vl[:, :3] = vel - vh[:, :3].astype(np.float64)
+        vh[:, 3] = 1.0
+        self.pos[:n_own] = torch.from_numpy(ph).to(dev)
+        self.pos[cap:cap + n_own] = torch.from_numpy(pl).to(dev)
+        self.vel[:n_own] = torch.from_numpy(vh).to(dev)
+        self.vel[cap:cap + n_own] = torch.from_numpy(vl).to(dev)
+        self.id[:n_own] = torch.from_numpy(np.asarray(ids, dtype=np.int64).astype(np.int32)).to(dev)
+
+        if integrator == "andersen":
+            self.rng = hx.Rand48()
+            self.rng_state = torch.zeros(3 * 32 * 256, dtype=torch.int16, device=dev)
+            hx.check(self.lib.hx_rand48_seed(C.byref(self.rng), 32, 256, int(seed) + 7919 * rank, self._p(self.rng_state), self.st))
+            self.set_temperature(temperature, rate)
+        self.lists_valid = False
+        self.force_valid = False
+        self.pending_finalize = False
+        self.last_interval, self.since_update = 16, 0
+        self.min_chunk, self.max_chunk = 2, 64
+
+    # ---- helpers ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def _p(t, offset=0):
+        return C.c_void_p(t.data_ptr() + offset * t.element_size() * (t.shape[1] if t.dim() > 1 else 1))
+
+    def set_timestep(self, dt):
+        self.dt = float(dt)
+        if self.kind == "andersen":
+            self.set_temperature(self.temperature, self.rate)
+
+    def set_temperature(self, temperature, rate):
+        self.temperature, self.rate = float(temperature), float(rate)
+        self.sqrt_temperature = float(np.float32(math.sqrt(temperature)))
+        self.coll_prob = float(np.float32(rate * self.dt))
+
+    def set_integrator(self, kind, timestep=None, temperature=None, rate=None):
+        """Swap the integrator (as constructing a new mdsim.integrators.* on the same particle instance)."""
+        self._finish_step()
+        if kind == "andersen" and not hasattr(self, "rng"):
+            raise self.hx.HxError("construct with integrator='andersen' to allocate the RNG state")
+        self.kind = kind
+        if timestep is not None:
+            self.dt = float(timestep)
+        if kind == "andersen":
+            self.set_temperature(self.temperature if temperature is None else temperature,
+                                 self.rate if rate is None else rate)
+
+    def _sort_pairs(self, n, bits):
+        hx = self.hx
+        hx.check(self.lib.hx_iota_u32(self._p(self.index), n, self.st))
+        hx.check(self.lib.hx_sort_pairs_stable_u32(self._p(self.keys), self._p(self.index), n, bits,
+                                                   self._p(self.sort_scratch), self.sort_bytes, self.st), "sort")
+
+    def _permute(self, n):
+        """Gather the first n particles by self.index into the back buffers and swap."""
+        self.hx.check(self.lib.hx_dd_permute(self._p(self.index), n, self.cap, self._p(self.pos), self._p(self.pos_b),
+                                             self._p(self.vel), self._p(self.vel_b), self._p(self.image), self._p(self.image_b),
+                                             self._p(self.id), self._p(self.id_b), self.st), "permute")
+        self.pos, self.pos_b = self.pos_b, self.pos
+        self.vel, self.vel_b = self.vel_b, self.vel
+        self.image, self.image_b = self.image_b, self.image
+        self.id, self.id_b = self.id_b, self.id
+
+    # ---- list update: migration, order, ghosts, cells, lists -------------------------------------------------------
+    def _migrate(self):
+        hx, torch, dec, cap = self.hx, self.torch, self.dec, self.cap
+        if self.nranks == 1:
+            return
+        n = self.n_own
+        hx.check(self.lib.hx_dd_owner_keys(self._p(self.pos), n, float(dec.x0), float(dec.width), self.nranks, self.rank,
+                                           self._p(self.keys), self._p(self.counts), self.st), "owner_keys")
+        cnt = self.counts.cpu().numpy().astype(np.int64)
+        self.stats["syncs"] += 1
+        if cnt[3] != 0:
+            raise hx.HxError(f"rank {self.rank}: {cnt[3]} particles moved further than one slab between list updates")
+        n_stay, n_l, n_r = int(cnt[0]), int(cnt[1]), int(cnt[2])
+        if n_l + n_r > 0:
+            self._sort_pairs(n, 8)          # stable: [stay | leftward | rightward], memory order kept within each
+            self._permute(n)
+        from_right, from_left = self.ex.exchange_counts(n_l, n_r)
+        n_new = n_stay + from_right + from_left
+        if n_new > self.own_cap:
+            raise hx.HxError(f"rank {self.rank}: owned particles {n_new} exceed the capacity {self.own_cap}")
+        a, b = n_stay, n_stay + n_l           # send blocks [a, b) leftward and [b, n) rightward
+        c, d = n_stay, n_stay + from_right    # arrivals: [c, d) from the right, [d, n_new) from the left
+        # arrivals overwrite the send blocks, so the outgoing records are staged first
+        def blocks(lo, hi):
+            return [self.pos[lo:hi].clone(), self.pos[cap + lo:cap + hi].clone(), self.vel[lo:hi].clone(),
+                    self.vel[cap + lo:cap + hi].clone(), self.image[lo:hi].clone(), self.id[lo:hi].clone()]
+
+        def slots(lo, hi):
+            return [self.pos[lo:hi], self.pos[cap + lo:cap + hi], self.vel[lo:hi], self.vel[cap + lo:cap + hi],
+                    self.image[lo:hi], self.id[lo:hi]]
+        out_l, out_r = blocks(a, b), blocks(b, n)
+        in_r, in_l = slots(c, d), slots(d, n_new)
+        for k in range(6):
+            self.ex.sendrecv(out_l[k], out_r[k], in_r[k], in_l[k])
+        self.stats["migrated"] += n_l + n_r
+        self.n_own = n_new
+
+    def _order(self):
+        """sorts.hilbert order of the owned particles (global box, so the curve is the single-GPU one)."""
+        hx, n = self.hx, self.n_own
+        if not self.sorting or n == 0:
+            return
+        hx.check(self.lib.hx_hilbert_keys(self._p(self.pos), n, self.Lf, self.depth, self._p(self.keys), self.st), "hilbert")
+        self._sort_pairs(n, 3 * self.depth)
+        self._permute(n)
+
+    def _ghosts(self):
+        """Select the particles each neighbour needs, exchange them and append the arrivals behind the owned ones."""
+        hx, torch, dec = self.hx, self.torch, self.dec
+        self.n_ghost = 0
+        self.n_ghost_from = {"left": 0, "right": 0}
+        n = self.n_own
+        counts = {"left": 0, "right": 0}
+        for dest in ("left", "right"):
+            self.send_idx[dest] = torch.zeros(0, dtype=torch.int32, device=self.pos.device)
+            self.send_buf[dest] = torch.zeros(0, 4, dtype=torch.float32, device=self.pos.device)
+        for side, dest in dec.ghost_sides():
+            hx.check(self.lib.hx_dd_ghost_keys(self._p(self.pos), n, float(dec.lo), float(dec.hi), float(dec.halo), side,
+                                               self._p(self.keys), self._p(self.counts), self.st), "ghost_keys")
+            self._sort_pairs(n, 8)
+            m = int(self.counts[0].item())
+            self.stats["syncs"] += 1
+            self.send_idx[dest] = self.index[:m].clone()
+            self.send_buf[dest] = torch.empty(m, 4, dtype=torch.float32, device=self.pos.device)
+            counts[dest] = m
+        if self.nranks == 1:
+            return
+        from_right, from_left = self.ex.exchange_counts(counts["left"], counts["right"])
+        total = n + from_right + from_left
+        if total > self.cap:
+            raise hx.HxError(f"rank {self.rank}: owned + ghost particles {total} exceed the capacity {self.cap}")
+        self.n_ghost_from = {"right": from_right, "left": from_left}
+        self.n_ghost = from_right + from_left
+        self._halo_exchange(guard=False)
+        # ghost ids (diagnostics, neighbour-set parity tests)
+        ids = {}
+        for dest in ("left", "right"):
+            ids[dest] = torch.empty(counts[dest], dtype=torch.int32, device=self.pos.device)
+            if counts[dest]:
+                hx.check(self.lib.hx_gather_u32(self._p(self.id), self._p(self.send_idx[dest]), counts[dest], self._p(ids[dest]), self.st))
+        self.ex.sendrecv(ids["left"], ids["right"], self.id[n:n + from_right], self.id[n + from_right:total])
+
+    def _halo_exchange(self, guard=True):
+        """Current positions (high words, species tag) of the fixed ghost sets: pack, exchange, land in the ghost slots."""
+        if self.nranks == 1:
+            return
+        hx, n = self.hx, self.n_own
+        ctl = self._p(self.ctl) if guard else None
+        for dest in ("left", "right"):
+            m = self.send_idx[dest].shape[0]
+            if m:
+                hx.check(self.lib.hx_gather_float4(self._p(self.pos), self._p(self.send_idx[dest]), m, self._p(self.send_buf[dest]), ctl, self.st))
+        fr, fl = self.n_ghost_from["right"], self.n_ghost_from["left"]
+        self.ex.sendrecv(self.send_buf["left"], self.send_buf["right"], self.pos[n:n + fr], self.pos[n + fr:n + fr + fl])
+
+    def _build(self):
+        hx, torch = self.hx, self.torch
+        ntot = self.n_own + self.n_ghost
+        while True:
+            self.flags.zero_()
+            hx.check(self.lib.hx_binning_update(self._p(self.pos), ntot, self.cell_length, self.ncell, self.cell_size, self._p(self.g_cell),
+                                                self._p(self.cell_count), None, self._p(self.flags), self.st), "binning")
+            hx.check(self.lib.hx_nlist_build2(self._p(self.g_cell), self.ncell, self.cell_size, self._p(self.pos), ntot, self.n_own,
+                                              self.rr_cut_skin, self.nt, self.nt, self.Lf, self._p(self.nl), self.size, self.stride,
+                                              hx.LAYOUT_ROW, 0, self._p(self.nl_count), self._p(self.flags, 1), self.st), "nlist")
+            fl = self.flags.cpu().numpy()
+            self.stats["syncs"] += 1
+            # every rank must take the same decision: the cell grid and list size are global properties
+            both = torch.tensor([int(fl[0]), int(fl[1])], dtype=torch.int32, device=self.pos.device)
+            self.ex.allreduce(both, "max")
+            f0, f1 = (int(v) for v in both.cpu().numpy())
+            if f0:
+                # binning.cpp:216-219 — overcrowded cells: double the cell size
+                self.cell_size *= 2
+                self.g_cell = torch.empty(self.ncells * self.cell_size, dtype=torch.int32, device=self.pos.device)
+                continue
+            if f1:
+                # from_binning.cpp:277-280 — overcrowded lists: halve the occupancy
+                self.occ_n /= 2
+                size = C.c_uint()
+                hx.check(self.lib.hx_nlist_plan(self.r_cut_max, self.skin, self.n_global, float(np.prod(self.L)), self.occ_n,
+                                                self.cell_size, C.byref(size)))
+                self.size = size.value
+                self.stride = ((self.size + 32) // 32) * 32
+                self.nl = torch.empty(self.own_cap * self.stride, dtype=torch.int32, device=self.pos.device)
+                continue
+            break
+
+    def update_lists(self):
+        """neighbour update: on_prepend_update (migration + sort) -> binning -> lists -> displacement zero."""
+        hx = self.hx
+        self._migrate()
+        self._order()
+        self._ghosts()
+        self._build()
+        hx.check(self.lib.hx_displacement_zero(self._p(self.pos), self._p(self.r0), self.n_own, self.st))
+        hx.check(self.lib.hx_ctl_reset(self._p(self.ctl), self.st))
+        self.lists_valid = True
+        self.updates += 1
+
+    # ---- forces, integration ------------------------------------------------------------------------------------------
+    def _force(self, aux=False, guarded=False):
+        hx = self.hx
+        hx.check(self.lib.hx_pair_force2(C.byref(self.pot), self._p(self.pos), self._p(self.pos), self.n_own + self.n_ghost,
+                                         self._p(self.nl), self.size, self.stride, hx.LAYOUT_ROW, self.n_own, self.Lf, 1, 0.5,
+                                         self._p(self.force), self._p(self.en_pot) if aux else None,
+                                         self._p(self.stress) if aux else None, self.cap,
+                                         self._p(self.ctl) if guarded else None, self.skin_half, self.st), "pair_force")
+
+    def _verlet(self, finalize, integrate, guarded):
+        hx = self.hx
+        hx.check(self.lib.hx_verlet_finalize_integrate_range(
+            self._p(self.pos), self._p(self.image), self._p(self.vel), self._p(self.force), self.n_own, self.n_own, self.cap,
+            self.dt, self.Lf, int(finalize), int(integrate), self._p(self.r0) if integrate else None,
+            self._p(self.ctl) if (guarded or integrate) else None, self.st), "verlet")
+
+    def _andersen(self, guarded):
+        hx = self.hx
+        fn = self.lib.hx_andersen_finalize_guarded if guarded else self.lib.hx_andersen_finalize
+        args = [self._p(self.vel), self._p(self.force), self.n_own, self.cap, self.dt, self.sqrt_temperature, self.coll_prob,
+                C.byref(self.rng), self._p(self.rng_state)]
+        if guarded:
+            args.append(self._p(self.ctl))
+        hx.check(fn(*args, self.st), "andersen")
+
+    def _ensure_force(self):
+        if not self.lists_valid:
+            self.update_lists()
+            self.force_valid = False
+        if not self.force_valid:
+            self._force()
+            self.force_valid = True
+
+    def _finish_step(self):
+        if self.pending_finalize:
+            self._verlet(True, False, False)
+            self.pending_finalize = False
+
+    def run(self, steps):
+        """sampler:run(steps): chunks of speculatively enqueued steps with the device-resident rebuild test."""
+        hx, torch = self.hx, self.torch
+        steps = int(steps)
+        if steps <= 0:
+            return
+        self._ensure_force()
+        fuse = self.kind == "verlet"
+        remaining = steps
+        while remaining > 0:
+            predicted = max(self.last_interval - self.since_update, 1)
+            chunk = int(min(max(self.min_chunk, min(self.max_chunk, predicted + 2)), remaining))
+            self.ctl[1:3].zero_()          # halted flag and step counter; the running displacement maximum stays
+            for k in range(chunk):
+                self._verlet(fuse and (self.pending_finalize or k > 0), True, True)
+                if self.nranks > 1:
+                    self._halo_exchange(guard=True)
+                    self.ex.allreduce(self.ctl[0:1], "max")     # rebuild vote: every rank sees the global maximum
+                self._force(guarded=True)
+                if not fuse:
+                    self._andersen(True)
+            ctl = self.ctl.cpu().numpy()
+            self.stats["chunks"] += 1
+            self.stats["syncs"] += 1
+            done, halted = int(ctl[2]), bool(ctl[1])
+            self.since_update += done
+            if halted:
+                self.last_interval = max(self.since_update + 1, 1)
+                self.update_lists()
+                self._force()
+                if not fuse:
+                    self._andersen(False)
+                done += 1
+                self.since_update = 0
+            elif self.since_update > self.last_interval:
+                self.last_interval = self.since_update
+            if fuse:
+                self.pending_finalize = True
+            remaining -= done
+            self.step += done
+        self._finish_step()
+        self.force_valid = True
+
+    # ---- observables ------------------------------------------------------------------------------------------------------
+    def thermodynamics(self):
+        """observables.thermodynamics over all ranks (halmd/observables/thermodynamics.hpp:73-86)."""
+        hx = self.hx
+        self._finish_step()
+        if not self.lists_valid:
+            self.update_lists()
+        self._force(aux=True)
+        self.force_valid = True
+        hx.check(self.lib.hx_thermodynamics(self._p(self.vel), self._p(self.en_pot), self._p(self.stress), self.cap, self.n_own,
+                                            self._p(self.thermo), self.st), "thermodynamics")
+        t = self.thermo.clone()
+        self.ex.allreduce(t, "sum")
+        s = t.cpu().numpy()
+        N = float(self.n_global)
+        volume = float(np.prod(self.L))
+        en_kin, en_pot, virial = 0.5 * s[0] / N, s[5] / N, s[6] / N
+        temp = 2 * en_kin / 3
+        return {"kinetic_energy": en_kin, "potential_energy": en_pot, "virial": virial, "temperature": temp,
+                "pressure": N / volume * (temp + virial / 3), "internal_energy": en_kin + en_pot,
+                "center_of_mass_velocity": list(s[1:4] / s[4]), "density": N / volume}
+
+    def mean_list_length(self):
+        t = self.nl_count[:self.n_own].sum(dtype=self.torch.int64).to(self.torch.float64).reshape(1)
+        c = self.torch.tensor([float(self.n_own)], dtype=self.torch.float64, device=t.device)
+        self.ex.allreduce(t, "sum")
+        self.ex.allreduce(c, "sum")
+        return float(t.item() / c.item())
+
+    def local_state(self):
+        """Host copies of this rank's owned particles: ids, positions (double), velocities (double), forces."""
+        self._finish_step()
+        self._ensure_force()
+        n, cap = self.n_own, self.cap
+        ph, pl = self.pos[:n, :3].double().cpu().numpy(), self.pos[cap:cap + n, :3].double().cpu().numpy()
+        vh, vl = self.vel[:n, :3].double().cpu().numpy(), self.vel[cap:cap + n, :3].double().cpu().numpy()
+        return {"id": self.id[:n].cpu().numpy().astype(np.int64), "position": ph + pl, "velocity": vh + vl,
+                "force": self.force[:n, :3].cpu().numpy(), "image": self.image[:n, :3].cpu().numpy()}
+
+    def neighbour_sets(self):
+        """{global id: sorted global ids of its neighbours} for the owned particles (parity tests)."""
+        if not self.lists_valid:
+            self.update_lists()
+        n, ntot = self.n_own, self.n_own + self.n_ghost
+        ids = self.id[:ntot].cpu().numpy().astype(np.int64)
+        rows = self.nl[:n * self.stride].cpu().numpy().view(np.uint32).reshape(n, self.stride)
+        cnt = self.nl_count[:n].cpu().numpy()
+        return {int(ids[i]): np.sort(ids[rows[i, :cnt[i]]]) for i in range(n)}

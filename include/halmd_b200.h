@@ -257,6 +257,46 @@ int hx_andersen_finalize_guarded(hx_float4* velocity_dev, const hx_float4* force
                                  float sqrt_temperature, float coll_prob, const hx_rand48* rng,
                                  uint16_t* state_dev, const uint32_t* ctl_dev, void* stream);
 
+/* ---- range-limited variants (arrays that hold ghost particles behind the owned ones) ------------------------------
+ * Same kernels as hx_nlist_build / hx_pair_force_guarded / hx_verlet_finalize_integrate with explicit counts:
+ * lists are built for particles < nbuild only (the others are partners), partner indices are valid below nparticle2,
+ * and the integrator touches slots < nprocess only (array_size stays the offset of the low-word planes).
+ * ctl_dev may be NULL in hx_pair_force2 (unguarded). */
+int hx_nlist_build2(const uint32_t* g_cell_dev, const unsigned ncell[3], unsigned cell_size,
+                    const hx_float4* position_hi_dev, size_t nparticle, size_t nbuild, const float* rr_cut_skin,
+                    unsigned ntype1, unsigned ntype2, const float box_length[3], uint32_t* g_neighbour_dev,
+                    unsigned size, size_t stride, int layout, int fill_all, uint32_t* count_dev,
+                    int* overflow_flag_dev, void* stream);
+int hx_pair_force2(const hx_lj_params* potential, const hx_float4* position1_hi_dev,
+                   const hx_float4* position2_hi_dev, size_t nparticle2, const uint32_t* g_neighbour_dev,
+                   unsigned size, size_t stride, int layout, size_t nparticle, const float box_length[3],
+                   int force_zero, float aux_weight, hx_float4* force_dev, float* en_pot_dev, float* stress_dev,
+                   size_t stress_stride, uint32_t* ctl_dev, float skin_half, void* stream);
+int hx_verlet_finalize_integrate_range(hx_float4* position_dev, hx_float4* image_dev, hx_float4* velocity_dev,
+                                       const hx_float4* force_dev, size_t nparticle, size_t nprocess,
+                                       size_t array_size, float timestep, const float box_length[3],
+                                       int do_finalize, int do_integrate, const hx_float4* r0_dev,
+                                       uint32_t* ctl_dev, void* stream);
+
+/* ---- slab domain decomposition (new; the reference is single-GPU, doc/usage/multi-gpu.rst.in) ---------------------
+ * Rank r of nranks owns wrapped x in [x0 + r*width, x0 + (r+1)*width).  Selections are produced as small integer
+ * keys for hx_sort_pairs_stable_u32 so that migrants and ghosts keep their memory order (deterministic).
+ * hx_dd_owner_keys: 0 stays, 1 to rank-1, 2 to rank+1 (1 for both when nranks == 2), 3 lost; counts_dev[4] histogram.
+ * hx_dd_ghost_keys: 0 if within `halo` of the low (side 0), high (side 1) or either (side 2) face, else 1.
+ * hx_dd_permute: out[i] = in[index[i]], i < nparticle, for position/velocity (hi and lo planes), image and id. */
+int hx_dd_owner_keys(const hx_float4* position_hi_dev, size_t nparticle, float x0, float width, int nranks, int rank,
+                     uint32_t* keys_dev, uint32_t* counts_dev, void* stream);
+int hx_dd_ghost_keys(const hx_float4* position_hi_dev, size_t nparticle, float lo, float hi, float halo, int side,
+                     uint32_t* keys_dev, uint32_t* count_dev, void* stream);
+int hx_dd_permute(const uint32_t* index_dev, size_t nparticle, size_t array_size, const hx_float4* position_in_dev,
+                  hx_float4* position_out_dev, const hx_float4* velocity_in_dev, hx_float4* velocity_out_dev,
+                  const hx_float4* image_in_dev, hx_float4* image_out_dev, const uint32_t* id_in_dev,
+                  uint32_t* id_out_dev, void* stream);
+/* dst[i] = src[index[i]]; the float4 variant returns at once when ctl_dev (may be NULL) is halted */
+int hx_gather_float4(const hx_float4* src_dev, const uint32_t* index_dev, size_t n, hx_float4* dst_dev,
+                     const uint32_t* ctl_dev, void* stream);
+int hx_gather_u32(const uint32_t* src_dev, const uint32_t* index_dev, size_t n, uint32_t* dst_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
