@@ -605,6 +605,21 @@ class DecomposedSystem:
         return {"id": self.id[:n].cpu().numpy().astype(np.int64), "position": ph + pl, "velocity": vh + vl,
                 "force": self.force[:n, :3].cpu().numpy(), "image": self.image[:n, :3].cpu().numpy()}
 
+    def upload(self, positions, velocities):
+        """Replace positions and velocities of the owned particles (same order as local_state()) from host arrays
+        (double, split into double-single words); as particle:set(), this invalidates lists and forces."""
+        torch, n, cap = self.torch, self.n_own, self.cap
+        self._finish_step()
+        dev = self.pos.device
+        for arr, host in ((self.pos, positions), (self.vel, velocities)):
+            host = np.asarray(host, dtype=np.float64)
+            hi = host.astype(np.float32)
+            lo = (host - hi.astype(np.float64)).astype(np.float32)
+            arr[:n, :3] = torch.from_numpy(hi).to(dev, non_blocking=True)
+            arr[cap:cap + n, :3] = torch.from_numpy(lo).to(dev, non_blocking=True)
+        self.lists_valid = False
+        self.force_valid = False
+
     def neighbour_sets(self):
         """{global id: sorted global ids of its neighbours} for the owned particles (parity tests)."""
         if not self.lists_valid:

@@ -11,7 +11,9 @@ import numpy as np
 from .api import mdsim, observables
 
 
-def fcc_positions(n, L):
+def fcc_lattice(n, L):
+    """Lattice constant, unit cells per dimension and number of sites to skip for n particles in a box L
+    (halmd/mdsim/gpu/positions/lattice.cpp:116-177)."""
     L = np.asarray(L, dtype=np.float64)
     u = 4
     a = (np.prod(L) / np.ceil(n / u)) ** (1.0 / 3)
@@ -23,22 +25,32 @@ def fcc_positions(n, L):
         ncell = np.maximum(m, np.floor(L / a).astype(np.int64))
         if np.all(m == ncell):
             ncell += 1
-    N = int(u * np.prod(ncell))
-    idx = np.arange(N, dtype=np.int64)
+    return a, ncell, int(u * np.prod(ncell))
+
+
+def fcc_sites(k, n, L, lattice=None):
+    """Positions of particles k (array of particle numbers in [0, n)) on the fcc lattice: surplus sites are left
+    vacant at regular intervals, then lattice_primitive.hpp:121-129 maps site index -> position."""
+    L = np.asarray(L, dtype=np.float64)
+    a, ncell, N = lattice or fcc_lattice(n, L)
+    k = np.asarray(k, dtype=np.int64)
     if N > n:
         skip = int(np.ceil(N / (N - n)))
-        keep = np.ones(N, dtype=bool)
-        keep[skip - 1::skip] = False
-        idx = idx[keep]
-    idx = idx[:n]
+        idx = k + k // (skip - 1)             # every skip-th site (skip-1, 2*skip-1, ...) stays vacant
+    else:
+        idx = k
     cell = idx >> 2
-    r = np.empty((n, 3), dtype=np.float64)
+    r = np.empty((len(k), 3), dtype=np.float64)
     r[:, 0] = cell % ncell[0] + (((idx ^ (idx >> 1)) & 1) * 2 + 1) / 4.0
     r[:, 1] = (cell // ncell[0]) % ncell[1] + ((idx & 1) * 2 + 1) / 4.0
     r[:, 2] = cell // (ncell[0] * ncell[1]) + ((idx & 2) + 1) / 4.0
     r *= a
     r += (L - ncell * a) / 2 - L / 2
     return r
+
+
+def fcc_positions(n, L):
+    return fcc_sites(np.arange(n, dtype=np.int64), n, L)
 
 
 def boltzmann_velocities(n, temperature, rng, mass=None):
@@ -114,6 +126,34 @@ def kob_andersen_mixture(n, density=1.2, temperature=0.7, timestep=0.001, skin=0
         integ = mdsim.integrators.verlet_nvt_andersen(box=box, particle=particle, timestep=timestep,
                                                       temperature=temperature, rate=rate, seed=seed)
     return System(box, particle, potential, force, integ)
+
+
+def decomposed_lj_fluid(n, rank, nranks, density=0.8442, temperature=1.2, cutoff=2.5, truncation="smooth_r4", h=0.005,
+                        timestep=0.001, skin=0.5, seed=1, integrator="verlet", rate=2.0, group=None, chunk=1 << 22,
+                        lanes=4):
+    """BASELINE config 4: one-component LJ fluid of n particles in total, slab-decomposed over `nranks` processes.
+    Every rank generates the lattice and the velocities chunk by chunk (same seeds everywhere) and keeps its slab, so
+    no rank ever holds the global state; particle ids are the lattice site numbers."""
+    from .decomposition import DecomposedSystem, SlabDecomposition
+    L = np.array([(n / density) ** (1.0 / 3)] * 3)
+    dec = SlabDecomposition(L, nranks, rank, cutoff + skin)
+    lattice = fcc_lattice(n, L)
+    pos, vel, ids = [], [], []
+    vsum = np.zeros(3)
+    for c, c0 in enumerate(range(0, n, chunk)):
+        k = np.arange(c0, min(n, c0 + chunk), dtype=np.int64)
+        r = fcc_sites(k, n, L, lattice).astype(np.float32)
+        v = np.random.default_rng([seed, c]).normal(scale=np.sqrt(temperature), size=(len(k), 3))
+        vsum += v.sum(axis=0)
+        mine = dec.slab_of(r[:, 0]) == rank
+        pos.append(r[mine].astype(np.float64))
+        vel.append(v[mine])
+        ids.append(k[mine])
+    pos, vel, ids = np.concatenate(pos), np.concatenate(vel), np.concatenate(ids)
+    vel -= vsum / n
+    return DecomposedSystem(L, pos, vel, ids, cutoff=(cutoff,), truncation=truncation, h=h, skin=skin, timestep=timestep,
+                            integrator=integrator, temperature=temperature, rate=rate, seed=seed, n_global=n, rank=rank,
+                            nranks=nranks, group=group, lanes=lanes)
 
 
 def smoke_check(hx, oracle, support, torch, np_):

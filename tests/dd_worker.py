@@ -111,7 +111,7 @@ def gpu_parity(rank, world, out):
     from halmd_b200.decomposition import DecomposedSystem, SlabDecomposition
     import torch.distributed as dist
 
-    torch.cuda.set_device(0)
+    torch.cuda.set_device(rank if os.environ.get("DD_BACKEND") == "nccl" else 0)
     n = int(os.environ.get("DD_N", "4000"))
     steps = int(os.environ.get("DD_STEPS", "100"))
     rho = 0.8442
@@ -157,7 +157,13 @@ def main():
     import torch.distributed as dist
     mode, out = sys.argv[1], sys.argv[2]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    backend = os.environ.get("DD_BACKEND", "gloo")
+    if backend == "nccl":
+        import torch
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         {"cpu_protocol": cpu_protocol, "gpu_parity": gpu_parity}[mode](rank, world, out)
     finally:

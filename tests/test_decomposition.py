@@ -137,11 +137,16 @@ def compare(ref, r, tag, n, bitwise, bitwise_force):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,n", [(1, 4000), (2, 4000), (3, 32000)])
-def test_decomposed_run_matches_single_gpu(tmp_path, world, n):
+@pytest.mark.parametrize("world,n,backend", [(1, 4000, "gloo"), (2, 4000, "gloo"), (3, 32000, "gloo"), (2, 32000, "nccl")])
+def test_decomposed_run_matches_single_gpu(tmp_path, world, n, backend):
+    """backend gloo: all ranks share cuda:0 and stage exchanges through host memory (runs on a one-GPU box);
+    backend nccl: one GPU per rank, device-to-device exchange over NVLink (skipped below two GPUs)."""
+    import torch
+    if backend == "nccl" and torch.cuda.device_count() < world:
+        pytest.skip("needs one GPU per rank")
     steps = 600
     out = str(tmp_path / "dd.npz")
-    launch("gpu_parity", world, out, {"DD_N": str(n), "DD_STEPS": str(steps)}, timeout=600)
+    launch("gpu_parity", world, out, {"DD_N": str(n), "DD_STEPS": str(steps), "DD_BACKEND": backend}, timeout=600)
     r = np.load(out)
     a, b, updates = single_gpu_reference(n, steps)
     # initial state: same positions => identical neighbour sets (by particle id) and forces to 1e-6
