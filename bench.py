@@ -254,7 +254,9 @@ def force_kernel_roofline(s, args, torch, iters=20):
         par = pot.params
 
         def launch():
-            hx.check(lib.hx_pair_force(C.byref(par), pos, pos, lib.hxm_neighbour_device_ptr(nb._h), nb.size, nb.stride, nb.layout, n,
+            # positions have been through the integrator: same flag as the module layer passes in the step loop
+            hx.check(lib.hx_pair_force(C.byref(par), pos, pos, lib.hxm_neighbour_device_ptr(nb._h), nb.size, nb.stride,
+                                       nb.layout | hx.FORCE_POSITIONS_REDUCED, n,
                                        L, 1, 0.5, force.data_ptr(), None, None, p.array_size, st))
     times = []
     for i in range(iters + 3):

@@ -79,6 +79,9 @@ struct hxm_particle {
     uint64_t force_pos_ver = 0;      // position version the force array belongs to
     bool aux_enabled = true;         // particle.cpp:64 — enabled by default to allow sampling of the initial state
     bool aux_valid = false;
+    // every position lies in the primary cell [-L/2, L/2]: true once an integration step has reduced them, false
+    // after positions were written from outside (HX_FORCE_POSITIONS_REDUCED)
+    bool reduced = false;
 
     ~hxm_particle()
     {
@@ -293,14 +296,15 @@ struct hxm_force {
     {
         hxm_particle* p = particle;
         hx_float4* pos = reinterpret_cast<hx_float4*>(p->pos);
+        int const layout = neighbour->layout | (p->reduced ? HX_FORCE_POSITIONS_REDUCED : 0);
         if (ctl) {
             return hx_pair_force_guarded(&potential->p, pos, pos, neighbour->g_neighbour, neighbour->size,
-                                         neighbour->stride, neighbour->layout, p->n, Lf, 1, weight(),
+                                         neighbour->stride, layout, p->n, Lf, 1, weight(),
                                          reinterpret_cast<hx_float4*>(p->force), aux ? p->en_pot : nullptr,
                                          aux ? p->stress : nullptr, p->A, ctl, skin_half, p->st);
         }
         return hx_pair_force(&potential->p, pos, pos, neighbour->g_neighbour, neighbour->size, neighbour->stride,
-                             neighbour->layout, p->n, Lf, 1, weight(), reinterpret_cast<hx_float4*>(p->force),
+                             layout, p->n, Lf, 1, weight(), reinterpret_cast<hx_float4*>(p->force),
                              aux ? p->en_pot : nullptr, aux ? p->stress : nullptr, p->A, p->st);
     }
 
@@ -353,6 +357,7 @@ struct hxm_integrator {
                                     reinterpret_cast<hx_float4*>(p->vel), reinterpret_cast<hx_float4*>(p->force), p->A,
                                     static_cast<float>(timestep), Lf, p->st));
         p->pos_ver++;
+        p->reduced = true;
         return 0;
     }
 
@@ -427,6 +432,7 @@ struct hxm_core {
             unsigned chunk = std::min<uint64_t>(std::max(min_chunk, std::min(max_chunk, predicted + 2)), remaining);
             // reset halted flag and step counter, keep the running maximum displacement
             HXM_CUDA(cudaMemsetAsync(nb->ctl + CTL_HALTED, 0, 2 * sizeof(uint32_t), p->st));
+            p->reduced = true;      // the integration kernel reduces every position before the force kernel reads it
             for (unsigned k = 0; k < chunk; ++k) {
                 HXM_TRY(hx_verlet_finalize_integrate(
                     reinterpret_cast<hx_float4*>(p->pos), reinterpret_cast<hx_float4*>(p->image),
@@ -722,7 +728,7 @@ static int particle_io(hxm_particle* p, const char* name_c, void* host, bool set
     size_t n = p->n, A = p->A;
     if (name == "position" || name == "species") {
         HXM_TRY(particle_float4_io(p, p->pos, true, set, name == "species", host, 3));
-        if (set) p->pos_ver++;
+        if (set) { p->pos_ver++; p->reduced = false; }
         return 0;
     }
     if (name == "velocity" || name == "mass") {
@@ -741,7 +747,7 @@ static int particle_io(hxm_particle* p, const char* name_c, void* host, bool set
     }
     if (name == "position_ds") {
         HXM_TRY(particle_ds_io(p, p->pos, set, static_cast<double*>(host)));
-        if (set) p->pos_ver++;
+        if (set) { p->pos_ver++; p->reduced = false; }
         return 0;
     }
     if (name == "velocity_ds") return particle_ds_io(p, p->vel, set, static_cast<double*>(host));
@@ -786,7 +792,7 @@ int hxm_particle_get(hxm_particle* p, const char* name, void* host_data) { retur
 void* hxm_particle_device_ptr(hxm_particle* p, const char* name_c)
 {
     std::string name(name_c ? name_c : "");
-    if (name == "position") return p->pos;
+    if (name == "position") { p->reduced = false; return p->pos; }      // (the caller may write through the pointer)
     if (name == "velocity") return p->vel;
     if (name == "image") return p->image;
     if (name == "force") return p->force;

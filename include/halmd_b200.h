@@ -44,6 +44,11 @@ extern "C" {
 #define HX_LAYOUT_COLUMN 0  /* g_neighbour[k * stride + i]  (reference default)          */
 #define HX_LAYOUT_ROW    1  /* g_neighbour[i * stride + k]  (reference "unroll_force_loop",
                                stride = row pitch >= size)                               */
+/* OR-ed into the `layout` argument of the pair-force entry points: the caller vouches that every position passed
+ * (position1 and position2) lies in the primary cell [-L/2, L/2], as left by the integrator's periodic reduction
+ * (verlet_kernel.cu:60-62, box_kernel.cuh:37-45).  Particles farther than r_cut from all faces then skip the
+ * minimum-image arithmetic (same results: their pairs within the cutoff have image 0). */
+#define HX_FORCE_POSITIONS_REDUCED 0x100
 
 /* potential truncations (halmd/mdsim/gpu/potentials/pair/truncations/) */
 #define HX_TRUNC_SHARP     0

@@ -207,8 +207,13 @@ def test_displacement_bit_exact(hx, oracle, dev):
 # ---- a7 neighbour lists ----------------------------------------------------------------------------------------
 
 def build_lists(hx, oracle, dev, n, rho, seed, rc, skin, occ_bin, occ_list, species_frac=None, layout=0, fill_all=1,
-                jitter=0.12):
+                jitter=0.12, reduce=False):
     L, p, v, A = lj_fluid(n, rho, seed, species_frac, jitter)
+    if reduce:
+        # positions as the integrator leaves them: in the primary cell [-L/2, L/2]
+        Lf = L.astype(np.float32)
+        p[:n, :3] -= (np.rint(p[:n, :3] / Lf) * Lf).astype(np.float32)
+        assert np.all(np.abs(p[:n, :3]) <= 0.5 * Lf * (1 + 1e-6))
     nt = 1 if species_frac is None else 2
     rc = np.asarray(rc, dtype=np.float32).reshape(-1)
     ncell, cl, cs, size = plan(hx, n, L, float(rc.max()), skin, occ_bin, occ_list)
@@ -283,7 +288,7 @@ def test_neighbour_overflow_flag(hx, oracle, dev):
 
 # ---- a8-a11 pair force -----------------------------------------------------------------------------------------
 
-def run_force(hx, oracle, dev, s, trunc, aux, eps, sigma, cut, h=0.005, force_zero=1, lanes=8):
+def run_force(hx, oracle, dev, s, trunc, aux, eps, sigma, cut, h=0.005, force_zero=1, lanes=8, flags=0):
     n, A, nt = s["n"], s["A"], s["nt"]
     par = hx.LjParams()
     hx.check(hx.lib.hx_potential_lj_init(C.byref(par), nt, nt, hx.farr(eps), hx.farr(sigma), trunc, hx.farr(cut), h))
@@ -300,7 +305,7 @@ def run_force(hx, oracle, dev, s, trunc, aux, eps, sigma, cut, h=0.005, force_ze
     d_f, d_e, d_s = dev.up(f0), dev.up(e0), dev.up(s0)
     hx.check(hx.lib.hx_pair_force_set_lanes(lanes))
     hx.check(hx.lib.hx_pair_force(C.byref(par), dev.p(s["d_pos"]), dev.p(s["d_pos"]), dev.p(s["d_nl"]), s["size"],
-                                  s["stride"], s["layout"], n, hx.f3(s["L"]), force_zero, 0.5,
+                                  s["stride"], s["layout"] | flags, n, hx.f3(s["L"]), force_zero, 0.5,
                                   dev.p(d_f), dev.p(d_e) if aux else None, dev.p(d_s) if aux else None, A, dev.stream),
              "hx_pair_force")
     of, oe, os_ = f0.copy(), e0.copy(), s0.copy()
@@ -349,6 +354,25 @@ def test_pair_force_binary_mixture(hx, oracle, dev, layout, lanes):
                     jitter=0.08)
     f, e, st, of, oe, os_ = run_force(hx, oracle, dev, s, 2, aux=False, eps=eps, sigma=sigma, cut=[2.5] * 4, lanes=lanes)
     check_force(f, of, s["n"])
+
+
+@pytest.mark.parametrize("lanes", [2, 4, 8])
+@pytest.mark.parametrize("trunc", [0, 1, 2])
+@pytest.mark.parametrize("eps,sigma", [(1.0, 1.0), (1.3, 0.9)])
+def test_pair_force_packed_row_kernel(hx, oracle, dev, lanes, trunc, eps, sigma):
+    """The production kernel (row layout, no aux, one species: packed f32x2 stream) in every truncation, lane count
+    and parameter mode (epsilon = sigma = 1 selects the lennard_jones_simple arithmetic), and with the
+    reduced-positions fast path, which must not change a single bit."""
+    s = build_lists(hx, oracle, dev, 16000, 0.8442, 41 + lanes, [2.5 * sigma], 0.5, 0.5, 0.4, layout=1, fill_all=0, reduce=True)
+    f, e, st, of, oe, os_ = run_force(hx, oracle, dev, s, trunc, aux=False, eps=[eps], sigma=[sigma], cut=[2.5], lanes=lanes)
+    check_force(f, of, s["n"])
+    f2, *_ = run_force(hx, oracle, dev, s, trunc, aux=False, eps=[eps], sigma=[sigma], cut=[2.5], lanes=lanes,
+                       flags=hx.FORCE_POSITIONS_REDUCED)
+    assert f2.tobytes() == f.tobytes()
+    # compensated sums: the typical particle agrees with the oracle to float rounding of the result
+    d = np.linalg.norm(f[:s["n"], :3].astype(np.float64) - of[:s["n"], :3].astype(np.float64), axis=1)
+    mag = np.linalg.norm(of[:s["n"], :3].astype(np.float64), axis=1)
+    assert np.mean(d / np.maximum(mag, 1e-30)) < 8 * EPS_F
 
 
 def test_pair_force_accumulate_onto_existing(hx, oracle, dev):
