@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhalmd_b200.so")
+# HALMD_B200_LIB: development aid (kernel build variants for A/B timing); the default is the in-tree build
+LIB_PATH = os.environ.get("HALMD_B200_LIB") or os.path.join(_HERE, "libhalmd_b200.so")
 
 PLACEHOLDER = 0xFFFFFFFF
 LAYOUT_COLUMN, LAYOUT_ROW = 0, 1

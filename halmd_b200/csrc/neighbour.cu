@@ -24,13 +24,15 @@ struct nlist_args {
     unsigned nbuild;           // lists are built for particles with index < nbuild (all others are partners only)
     size_t stride;
     vec3 L, invL;
-    unsigned ntype2;
+    unsigned ntype1, ntype2;
     int fill_all;
     float rr_cut_skin[HX_MAX_PAIR_TYPES];
 };
 
-constexpr unsigned NL_THREADS = 128;
+constexpr unsigned NL_THREADS = 256;
 constexpr unsigned NL_WARPS = NL_THREADS / 32;
+constexpr unsigned NL_CELLS_PER_WARP = (27 + NL_WARPS - 1) / NL_WARPS;
+constexpr unsigned NL_MAX_CHUNKS = 4;          // cell_size <= 128 keeps the staging loops fully unrolled
 
 __device__ __forceinline__ unsigned wrap_cell(int c, int d, int n)
 {
@@ -53,12 +55,85 @@ __device__ __forceinline__ void visit_offset(unsigned k, int& dx, int& dy, int& 
     dx = s * j0; dy = s * j1; dz = s * j2;
 }
 
+// Lists of the home cell's particles: distance tests over the staged candidates, ballot compaction, list stores.
+//   IMG   the minimum-image convention is applied.  It is skipped when the staged positions span less than half
+//         a box length in every direction: the image number of every pair is then exactly zero and
+//         d - 0 * L == d, so not a bit changes
+//   TYPED cutoff looked up per species pair
+template <bool ROW, bool IMG, bool TYPED>
+__device__ __forceinline__ void nlist_lists(nlist_args const& a, const float4* s_pos, const unsigned* s_id, const float* s_rr,
+                                            unsigned M, unsigned home_off, unsigned home_cnt)
+{
+    unsigned const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned const lane_lt = (1u << lane) - 1u;
+    float const rr_cut0 = a.rr_cut_skin[0];
+    for (unsigned p = warp; p < home_cnt; p += NL_WARPS) {
+        unsigned const n = s_id[home_off + p];
+        if (n >= a.nbuild) break;                  // ascending indices within a cell: the rest are partners only
+        float4 const r1 = s_pos[home_off + p];
+        unsigned* row = ROW ? a.g_neighbour + static_cast<size_t>(n) * a.stride : a.g_neighbour + n;
+        unsigned count = 0;
+        // two chunks per trip: independent shared-memory loads and distance chains in flight
+        for (unsigned base = 0; base < M; base += 64) {
+            unsigned count2 = count;
+            // (the second chunk's slots follow the first's: evaluate both tests, then compact in order)
+            bool ok0 = false, ok1 = false;
+            unsigned m0 = HX_PH, m1 = HX_PH;
+            unsigned const e0 = base + lane, e1 = base + 32 + lane;
+            float4 q0, q1;
+            if (e0 < M) { m0 = s_id[e0]; q0 = s_pos[e0]; }
+            if (e1 < M) { m1 = s_id[e1]; q1 = s_pos[e1]; }
+            if (e0 < M) {
+                float dx = __fsub_rn(r1.x, q0.x), dy = __fsub_rn(r1.y, q0.y), dz = __fsub_rn(r1.z, q0.z);
+                if (IMG) { dx = minimg(dx, a.L.x, a.invL.x); dy = minimg(dy, a.L.y, a.invL.y); dz = minimg(dz, a.L.z, a.invL.z); }
+                float const cut = TYPED ? s_rr[__float_as_uint(r1.w) * a.ntype2 + __float_as_uint(q0.w)] : rr_cut0;
+                ok0 = (m0 != n) && (norm2(dx, dy, dz) <= cut);          // note <= : from_binning_kernel.cu:143
+            }
+            if (e1 < M) {
+                float dx = __fsub_rn(r1.x, q1.x), dy = __fsub_rn(r1.y, q1.y), dz = __fsub_rn(r1.z, q1.z);
+                if (IMG) { dx = minimg(dx, a.L.x, a.invL.x); dy = minimg(dy, a.L.y, a.invL.y); dz = minimg(dz, a.L.z, a.invL.z); }
+                float const cut = TYPED ? s_rr[__float_as_uint(r1.w) * a.ntype2 + __float_as_uint(q1.w)] : rr_cut0;
+                ok1 = (m1 != n) && (norm2(dx, dy, dz) <= cut);
+            }
+            unsigned const mask0 = __ballot_sync(0xFFFFFFFFu, ok0);
+            unsigned const mask1 = __ballot_sync(0xFFFFFFFFu, ok1);
+            unsigned const slot0 = count2 + __popc(mask0 & lane_lt);
+            count2 += __popc(mask0);
+            unsigned const slot1 = count2 + __popc(mask1 & lane_lt);
+            count2 += __popc(mask1);
+            if (ok0 && slot0 < a.size) {
+                if (ROW) row[slot0] = m0;
+                else row[static_cast<size_t>(slot0) * a.stride] = m0;
+            }
+            if (ok1 && slot1 < a.size) {
+                if (ROW) row[slot1] = m1;
+                else row[static_cast<size_t>(slot1) * a.stride] = m1;
+            }
+            count = count2;
+        }
+        if (count >= a.size) {
+            // from_binning_kernel.cu:263-266 — list fully occupied ⇒ overcrowded
+            count = a.size;
+            if (lane == 0) *a.overflow = 1;
+        }
+        if (ROW) {
+            // terminate the row with placeholders up to the next multiple of 32 (or the whole pitch)
+            size_t end = a.fill_all ? a.stride : min(static_cast<size_t>((count + 32u) & ~31u), a.stride);
+            for (size_t k = count + lane; k < end; k += 32) row[k] = HX_PH;
+        }
+        if (a.count_out && lane == 0) a.count_out[n] = count;
+    }
+}
+
 template <bool ROW>
 __global__ void __launch_bounds__(NL_THREADS) k_nlist_build(nlist_args a)
 {
     extern __shared__ float4 s_dyn[];
     __shared__ unsigned s_cnt[27];
     __shared__ unsigned s_off[28];
+    __shared__ unsigned s_cell[27];
+    __shared__ float s_rr[HX_MAX_PAIR_TYPES];
+    __shared__ float s_ext[NL_WARPS][6];
 
     unsigned const cell = blockIdx.x;
     unsigned const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -74,89 +149,109 @@ __global__ void __launch_bounds__(NL_THREADS) k_nlist_build(nlist_args a)
 
     float4* s_pos = s_dyn;                                             // [27*cs] (x, y, z, species)
     unsigned* s_id = reinterpret_cast<unsigned*>(s_dyn + 27 * cs);     // [27*cs]
+    if (threadIdx.x < HX_MAX_PAIR_TYPES) s_rr[threadIdx.x] = a.rr_cut_skin[threadIdx.x];
 
-    // phase 1: occupancy of the 27 cells
-    for (unsigned k = warp; k < 27; k += NL_WARPS) {
-        int dx, dy, dz;
-        visit_offset(k, dx, dy, dz);
-        unsigned c = (wrap_cell(cz, dz, a.ncell.z) * a.ncell.y + wrap_cell(cy, dy, a.ncell.y)) * a.ncell.x
-                     + wrap_cell(cx, dx, a.ncell.x);
-        const unsigned* src = a.g_cell + static_cast<size_t>(c) * cs;
-        unsigned cnt = 0;
-        for (unsigned base = 0; base < cs; base += 32) {
-            unsigned m = __ballot_sync(0xFFFFFFFFu, src[base + lane] != HX_PH);
-            cnt += __popc(m);
-            if (m != 0xFFFFFFFFu) break;
+    // phase 1: occupancy of the 27 cells; the loads of a warp's cells are independent and issued together
+    unsigned const nchunk = cs / 32;
+#pragma unroll
+    for (unsigned kk = 0; kk < NL_CELLS_PER_WARP; ++kk) {
+        unsigned const k = warp + kk * NL_WARPS;
+        if (k < 27) {
+            int dx, dy, dz;
+            visit_offset(k, dx, dy, dz);
+            unsigned const c = (wrap_cell(cz, dz, a.ncell.z) * a.ncell.y + wrap_cell(cy, dy, a.ncell.y)) * a.ncell.x
+                               + wrap_cell(cx, dx, a.ncell.x);
+            const unsigned* src = a.g_cell + static_cast<size_t>(c) * cs;
+            unsigned cnt = 0;
+            if (nchunk <= NL_MAX_CHUNKS) {
+                unsigned v[NL_MAX_CHUNKS];
+#pragma unroll
+                for (unsigned u = 0; u < NL_MAX_CHUNKS; ++u) v[u] = (u < nchunk) ? src[u * 32 + lane] : HX_PH;
+#pragma unroll
+                for (unsigned u = 0; u < NL_MAX_CHUNKS; ++u) cnt += __popc(__ballot_sync(0xFFFFFFFFu, v[u] != HX_PH));
+            } else {
+                for (unsigned base = 0; base < cs; base += 32) {
+                    unsigned m = __ballot_sync(0xFFFFFFFFu, src[base + lane] != HX_PH);
+                    cnt += __popc(m);
+                    if (m != 0xFFFFFFFFu) break;
+                }
+            }
+            if (lane == 0) { s_cnt[k] = cnt; s_cell[k] = c; }
         }
-        if (lane == 0) s_cnt[k] = cnt;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned o = 0;
-        for (unsigned k = 0; k < 27; ++k) { s_off[k] = o; o += s_cnt[k]; }
-        s_off[27] = o;
+    if (warp == 0) {
+        // exclusive scan of the 27 counts
+        unsigned const c = lane < 27 ? s_cnt[lane] : 0u;
+        unsigned incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= static_cast<unsigned>(o)) incl += t;
+        }
+        if (lane < 28) s_off[lane] = incl - c;      // lane 27: total
     }
     __syncthreads();
-    // phase 2: stage ids and positions, packed in visiting order
-    for (unsigned k = warp; k < 27; k += NL_WARPS) {
-        int dx, dy, dz;
-        visit_offset(k, dx, dy, dz);
-        unsigned c = (wrap_cell(cz, dz, a.ncell.z) * a.ncell.y + wrap_cell(cy, dy, a.ncell.y)) * a.ncell.x
-                     + wrap_cell(cx, dx, a.ncell.x);
-        const unsigned* src = a.g_cell + static_cast<size_t>(c) * cs;
-        unsigned cnt = s_cnt[k], off = s_off[k];
-        for (unsigned e = lane; e < cnt; e += 32) {
-            unsigned id = src[e];
-            s_id[off + e] = id;
-            s_pos[off + e] = __ldg(&a.pos_hi[id]);
+    // phase 2: stage ids and positions, packed in visiting order; ids (L1/L2 hits now) and the dependent position
+    // gathers of all of a warp's cells are in flight together.  Each lane tracks the extent of what it staged.
+    float const big = 3.0e38f;
+    float lo_x = big, lo_y = big, lo_z = big, hi_x = -big, hi_y = -big, hi_z = -big;
+    auto stage = [&](unsigned slot, unsigned id) {
+        float4 const r = __ldg(&a.pos_hi[id]);
+        s_id[slot] = id;
+        s_pos[slot] = r;
+        lo_x = fminf(lo_x, r.x); hi_x = fmaxf(hi_x, r.x);
+        lo_y = fminf(lo_y, r.y); hi_y = fmaxf(hi_y, r.y);
+        lo_z = fminf(lo_z, r.z); hi_z = fmaxf(hi_z, r.z);
+    };
+#pragma unroll
+    for (unsigned kk = 0; kk < NL_CELLS_PER_WARP; ++kk) {
+        unsigned const k = warp + kk * NL_WARPS;
+        if (k < 27) {
+            const unsigned* src = a.g_cell + static_cast<size_t>(s_cell[k]) * cs;
+            unsigned const cnt = s_cnt[k], off = s_off[k];
+            if (nchunk <= NL_MAX_CHUNKS) {
+#pragma unroll
+                for (unsigned u = 0; u < NL_MAX_CHUNKS; ++u) {
+                    unsigned const e = u * 32 + lane;
+                    if (e < cnt) stage(off + e, src[e]);
+                }
+            } else {
+                for (unsigned e = lane; e < cnt; e += 32) stage(off + e, src[e]);
+            }
         }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo_x = fminf(lo_x, __shfl_xor_sync(0xFFFFFFFFu, lo_x, o)); hi_x = fmaxf(hi_x, __shfl_xor_sync(0xFFFFFFFFu, hi_x, o));
+        lo_y = fminf(lo_y, __shfl_xor_sync(0xFFFFFFFFu, lo_y, o)); hi_y = fmaxf(hi_y, __shfl_xor_sync(0xFFFFFFFFu, hi_y, o));
+        lo_z = fminf(lo_z, __shfl_xor_sync(0xFFFFFFFFu, lo_z, o)); hi_z = fmaxf(hi_z, __shfl_xor_sync(0xFFFFFFFFu, hi_z, o));
+    }
+    if (lane == 0) {
+        s_ext[warp][0] = lo_x; s_ext[warp][1] = lo_y; s_ext[warp][2] = lo_z;
+        s_ext[warp][3] = hi_x; s_ext[warp][4] = hi_y; s_ext[warp][5] = hi_z;
     }
     __syncthreads();
 
     unsigned const M = s_off[27];
     unsigned const home_off = s_off[26], home_cnt = s_cnt[26];
-
-    for (unsigned p = warp; p < home_cnt; p += NL_WARPS) {
-        unsigned const n = s_id[home_off + p];
-        if (n >= a.nbuild) break;                  // ascending indices within a cell: the rest are partners only
-        float4 const r1 = s_pos[home_off + p];
-        unsigned const type1 = __float_as_uint(r1.w);
-        unsigned* row = ROW ? a.g_neighbour + static_cast<size_t>(n) * a.stride : a.g_neighbour + n;
-        unsigned count = 0;
-        for (unsigned base = 0; base < M; base += 32) {
-            unsigned e = base + lane;
-            bool ok = false;
-            unsigned m = HX_PH;
-            if (e < M) {
-                m = s_id[e];
-                float4 r2 = s_pos[e];
-                float dx = minimg(__fsub_rn(r1.x, r2.x), a.L.x, a.invL.x);
-                float dy = minimg(__fsub_rn(r1.y, r2.y), a.L.y, a.invL.y);
-                float dz = minimg(__fsub_rn(r1.z, r2.z), a.L.z, a.invL.z);
-                float rr = norm2(dx, dy, dz);
-                unsigned type2 = __float_as_uint(r2.w);
-                // note <= : from_binning_kernel.cu:143
-                ok = (m != n) && (rr <= a.rr_cut_skin[type1 * a.ntype2 + type2]);
-            }
-            unsigned mask = __ballot_sync(0xFFFFFFFFu, ok);
-            unsigned slot = count + __popc(mask & ((1u << lane) - 1u));
-            if (ok && slot < a.size) {
-                if (ROW) row[slot] = m;
-                else row[static_cast<size_t>(slot) * a.stride] = m;
-            }
-            count += __popc(mask);
-        }
-        if (count >= a.size) {
-            // from_binning_kernel.cu:263-266 — list fully occupied ⇒ overcrowded
-            count = a.size;
-            if (lane == 0) *a.overflow = 1;
-        }
-        if (ROW) {
-            // terminate the row with placeholders up to the next multiple of 32 (or the whole pitch)
-            size_t end = a.fill_all ? a.stride : min(static_cast<size_t>((count + 32u) & ~31u), a.stride);
-            for (size_t k = count + lane; k < end; k += 32) row[k] = HX_PH;
-        }
-        if (a.count_out && lane == 0) a.count_out[n] = count;
+    // extent of the staged positions (the same value in every thread)
+    float ext[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        float v = s_ext[0][c];
+#pragma unroll
+        for (unsigned w = 1; w < NL_WARPS; ++w) v = c < 3 ? fminf(v, s_ext[w][c]) : fmaxf(v, s_ext[w][c]);
+        ext[c] = v;
+    }
+    bool const interior = ext[3] - ext[0] < 0.49f * a.L.x && ext[4] - ext[1] < 0.49f * a.L.y && ext[5] - ext[2] < 0.49f * a.L.z;
+    bool const typed = a.ntype2 * a.ntype1 > 1;
+    if (typed) {
+        if (interior) nlist_lists<ROW, false, true>(a, s_pos, s_id, s_rr, M, home_off, home_cnt);
+        else nlist_lists<ROW, true, true>(a, s_pos, s_id, s_rr, M, home_off, home_cnt);
+    } else {
+        if (interior) nlist_lists<ROW, false, false>(a, s_pos, s_id, s_rr, M, home_off, home_cnt);
+        else nlist_lists<ROW, true, false>(a, s_pos, s_id, s_rr, M, home_off, home_cnt);
     }
 }
 
@@ -215,6 +310,7 @@ static int nlist_build_impl(const uint32_t* g_cell_dev, const unsigned ncell[3],
     a.stride = stride;
     a.L = make_vec3(box_length);
     a.invL = {1.0f / box_length[0], 1.0f / box_length[1], 1.0f / box_length[2]};
+    a.ntype1 = ntype1;
     a.ntype2 = ntype2;
     a.fill_all = fill_all;
     for (unsigned i = 0; i < HX_MAX_PAIR_TYPES; ++i) a.rr_cut_skin[i] = (i < ntype1 * ntype2) ? rr_cut_skin[i] : 0.f;

@@ -27,7 +27,7 @@ def sorted_lists(s):
     return torch.from_numpy(rows.view(np.int32).copy()).cuda()
 
 
-def time_force(s, lanes, flush, iters=20, lists=None):
+def time_force(s, lanes, flush, iters=20, lists=None, flags=0):
     lib = hx.lib
     p, nb, pot = s.particle, s.neighbour, s.potential
     hx.check(lib.hx_pair_force_set_lanes(lanes))
@@ -44,7 +44,7 @@ def time_force(s, lanes, flush, iters=20, lists=None):
             fl.fill_(float(i))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        hx.check(lib.hx_pair_force(C.byref(par), pos, pos, (lists.data_ptr() if lists is not None else lib.hxm_neighbour_device_ptr(nb._h)), nb.size, nb.stride, nb.layout, n,
+        hx.check(lib.hx_pair_force(C.byref(par), pos, pos, (lists.data_ptr() if lists is not None else lib.hxm_neighbour_device_ptr(nb._h)), nb.size, nb.stride, nb.layout | flags, n,
                                    L, 1, 0.5, force.data_ptr(), None, None, p.array_size, C.c_void_p(stream.cuda_stream)))
         e1.record(stream)
         torch.cuda.synchronize()
@@ -57,9 +57,26 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--sorted", action="store_true", help="also time the row kernel on index-sorted rows")
+    ap.add_argument("--quick", action="store_true", help="row layout, packed kernel only: lanes x reduced-positions flag")
     a = ap.parse_args()
     cfg = bench.CONFIGS[a.config]
     out = []
+    if a.quick:
+        args = argparse.Namespace(layout="row", melt_steps=2000)
+        s = bench.build_system(args, cfg, seed=1)
+        s.run(200)
+        s.neighbour.check()
+        for lanes in (2, 4, 8):
+            for flags in (0, hx.FORCE_POSITIONS_REDUCED):
+                avg, best = time_force(s, lanes, True, flags=flags)
+                print(json.dumps(dict(lib=os.path.basename(hx.LIB_PATH), lanes=lanes, reduced=int(flags != 0), avg_us=round(avg, 2),
+                                      min_us=round(best, 2))), flush=True)
+        if a.sorted:
+            srt = sorted_lists(s)
+            for lanes in (2, 4, 8):
+                avg, best = time_force(s, lanes, True, lists=srt, flags=hx.FORCE_POSITIONS_REDUCED)
+                print(json.dumps(dict(sorted_rows=True, lanes=lanes, avg_us=round(avg, 2), min_us=round(best, 2))), flush=True)
+        return
     for layout in ("row", "column"):
         args = argparse.Namespace(layout=layout, melt_steps=2000)
         s = bench.build_system(args, cfg, seed=1)
