@@ -197,7 +197,7 @@ def smoke_check(hx, oracle, support, torch, np_):
     d = np_.linalg.norm(f.astype(np_.float64) - of[:n, :3], axis=1)
     mag = np_.linalg.norm(of[:n, :3].astype(np_.float64), axis=1)
     rel = float((d / np_.maximum(mag, np_.sqrt((mag ** 2).mean()))).max())
-    assert rel < 1e-6, rel
+    assert rel < 3e-6, rel      # IEEE oracle vs the reference's MUFU arithmetic mirrored by the kernels (tests/test_gpu_kernels.py)
     # a fresh list build at the current positions must reproduce the oracle's sets exactly
     fresh = lennard_jones_fluid(n, seed=3, disable_sorting=True, shuffle=False)
     fresh.particle.set("position", pos)

@@ -1,0 +1,288 @@
+// refgpu.cpp — host-array launchers for the REFERENCE's own CUDA kernels (oracle/_ref/libhalmd_ref_gpu.so).
+// TEST INFRASTRUCTURE ONLY: loaded by tests/ (and nothing else) to compare the product's kernels with the reference's.
+//
+// The reference's kernel translation units (halmd/mdsim/gpu/**/*_kernel.cu) are compiled by nvcc where they lie under
+// /root/reference — unmodified, nothing copied — for sm_100a with the reference's own flags
+// (-ftz=true -prec-div=false -prec-sqrt=false --fmad=true, cmake/platform.cmake:75); see oracle/Makefile.  This file is
+// the host side, compiled by g++ like the reference's host classes: it fills device arrays and textures the way those
+// classes do and launches through the same `*_wrapper::kernel` cuda::function objects (file:line cited per function).
+// Every entry point takes HOST arrays and is synchronous.  Return value: 0 or a cudaError_t.
+#include <halmd/config.hpp>
+#include <halmd/mdsim/gpu/binning_kernel.hpp>
+#include <halmd/mdsim/gpu/forces/pair_trunc_kernel.hpp>
+#include <halmd/mdsim/gpu/integrators/verlet_kernel.hpp>
+#include <halmd/mdsim/gpu/max_displacement_kernel.hpp>
+#include <halmd/mdsim/gpu/neighbours/from_binning_kernel.hpp>
+#include <halmd/mdsim/gpu/potentials/pair/lennard_jones_kernel.hpp>
+#include <halmd/mdsim/gpu/potentials/pair/truncations/sharp_kernel.hpp>
+#include <halmd/mdsim/gpu/potentials/pair/truncations/shifted_kernel.hpp>
+#include <halmd/mdsim/gpu/potentials/pair/truncations/smooth_r4_kernel.hpp>
+#include <halmd/mdsim/gpu/sorts/hilbert_kernel.hpp>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+using namespace halmd;
+using namespace halmd::mdsim::gpu;
+
+#define RG_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "refgpu: %s: %s\n", #x, cudaGetErrorString(e_)); return static_cast<int>(e_); } } while (0)
+#define RG_TRY(stmt) try { stmt; } catch (std::exception const& e) { fprintf(stderr, "refgpu: %s\n", e.what()); return -1; }
+
+namespace {
+
+template <typename T>
+struct dbuf {
+    T* p = nullptr;
+    size_t n = 0;
+    explicit dbuf(size_t n_) : n(n_) { if (cudaMalloc(&p, (n ? n : 1) * sizeof(T)) != cudaSuccess) p = nullptr; }
+    dbuf(const T* host, size_t n_) : dbuf(n_) { if (p && n && host) cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice); }
+    ~dbuf() { if (p) cudaFree(p); }
+    int down(T* host) const { return static_cast<int>(cudaMemcpy(host, p, n * sizeof(T), cudaMemcpyDeviceToHost)); }
+    dbuf(dbuf const&) = delete;
+    dbuf& operator=(dbuf const&) = delete;
+};
+
+// linear-memory texture object, built as cuda::texture<T>(vector) builds it (cuda_wrapper/texture.hpp:33-46)
+template <typename T>
+struct lintex {
+    cudaTextureObject_t t = 0;
+    lintex(const T* dev, size_t n)
+    {
+        cudaResourceDesc rd = {};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = const_cast<T*>(dev);
+        rd.res.linear.desc = cudaCreateChannelDesc<T>();
+        rd.res.linear.sizeInBytes = n * sizeof(T);
+        cudaTextureDesc td = {};
+        td.readMode = cudaReadModeElementType;
+        cudaCreateTextureObject(&t, &rd, &td, nullptr);
+    }
+    ~lintex() { if (t) cudaDestroyTextureObject(t); }
+};
+
+template <typename V>
+V vec3(const float* v) { V r; for (int d = 0; d < 3; ++d) r[d] = v[d]; return r; }
+
+} // namespace
+
+extern "C" {
+
+// from_binning::update (from_binning.cpp:186-240): lists pre-set to 0xFF, one block per cell, cell_size threads,
+// cell_size * (2 + dimension) * sizeof(int) bytes of shared memory.
+// layout 0: g_neighbour[k * stride + i] (default); layout 1: g_neighbour[i * size + k] (unroll_force_loop)
+int refgpu_nlist_build(const uint32_t* g_cell, const unsigned ncell[3], unsigned cell_size, const float* position4,
+                       size_t nposition, const float* rr_cut_skin, unsigned ntype1, unsigned ntype2, const float box_length[3],
+                       uint32_t* g_neighbour, unsigned size, size_t stride, int layout, int* overcrowded)
+{
+    size_t const ncells = static_cast<size_t>(ncell[0]) * ncell[1] * ncell[2];
+    size_t const nl_len = static_cast<size_t>(size) * stride;
+    dbuf<unsigned int> d_cell(g_cell, ncells * cell_size);
+    dbuf<float4> d_pos(reinterpret_cast<const float4*>(position4), nposition);
+    dbuf<float> d_rr(rr_cut_skin, ntype1 * ntype2);
+    dbuf<unsigned int> d_nl(nl_len);
+    dbuf<int> d_ret(1);
+    if (!d_cell.p || !d_pos.p || !d_rr.p || !d_nl.p || !d_ret.p) return static_cast<int>(cudaErrorMemoryAllocation);
+    RG_CHECK(cudaMemset(d_nl.p, 0xFF, nl_len * sizeof(unsigned int)));
+    RG_CHECK(cudaMemset(d_ret.p, 0, sizeof(int)));
+    lintex<float> t_rr(d_rr.p, ntype1 * ntype2);
+    lintex<float4> t_r(d_pos.p, nposition);
+    fixed_vector<unsigned int, 3> nc;
+    for (int d = 0; d < 3; ++d) nc[d] = ncell[d];
+    auto* kernel = &neighbours::from_binning_wrapper<3>::kernel.normal;
+    if (layout) kernel = &neighbours::from_binning_wrapper<3>::kernel.unroll_force_loop;
+    RG_TRY(
+        kernel->update_neighbours.configure(dim3(static_cast<unsigned>(ncells)), dim3(cell_size), cell_size * (2 + 3) * sizeof(int));
+        kernel->update_neighbours(t_rr.t, t_r.t, t_r.t, d_ret.p, d_nl.p, size, static_cast<unsigned>(stride), d_cell.p, d_cell.p,
+                                  ntype1, ntype2, static_cast<unsigned>(ncells * cell_size), nc,
+                                  vec3<fixed_vector<float, 3>>(box_length));
+    )
+    RG_CHECK(cudaDeviceSynchronize());
+    int ret = 0;
+    RG_CHECK(static_cast<cudaError_t>(d_ret.down(&ret)));
+    if (overcrowded) *overcrowded = ret;
+    return d_nl.down(g_neighbour);
+}
+
+// sorts::hilbert (hilbert.cpp:59, 88-101): depth symbol, then `map` over the whole particle array
+int refgpu_hilbert_map(const float* position4, size_t array_size, const float box_length[3], unsigned depth, uint32_t* keys)
+{
+    if (array_size % 128 != 0) return static_cast<int>(cudaErrorInvalidValue);
+    dbuf<float4> d_pos(reinterpret_cast<const float4*>(position4), array_size);
+    dbuf<unsigned int> d_key(array_size);
+    if (!d_pos.p || !d_key.p) return static_cast<int>(cudaErrorMemoryAllocation);
+    auto& kernel = sorts::hilbert_wrapper<3>::kernel;
+    RG_TRY(
+        kernel.depth.set(depth);
+        kernel.map.configure(dim3(static_cast<unsigned>(array_size / 128)), dim3(128));
+        kernel.map(d_pos.p, d_key.p, vec3<fixed_vector<float, 3>>(box_length));
+    )
+    RG_CHECK(cudaDeviceSynchronize());
+    return d_key.down(keys);
+}
+
+// max_displacement::compute (max_displacement.cpp:77-106): block maxima on the device, maximum over blocks on the host
+int refgpu_displacement_max(const float* position4, const float* r0_4, size_t nparticle, const float box_length[3], float* max_rr)
+{
+    unsigned const blocks = 64, threads = 128;
+    dbuf<float4> d_pos(reinterpret_cast<const float4*>(position4), nparticle);
+    dbuf<float4> d_r0(reinterpret_cast<const float4*>(r0_4), nparticle);
+    dbuf<float> d_rr(blocks);
+    if (!d_pos.p || !d_r0.p || !d_rr.p) return static_cast<int>(cudaErrorMemoryAllocation);
+    auto& kernel = max_displacement_wrapper<3>::kernel;
+    RG_TRY(
+        kernel.displacement.configure(dim3(blocks), dim3(threads));
+        kernel.displacement(d_pos.p, d_r0.p, d_rr.p, static_cast<unsigned>(nparticle), vec3<fixed_vector<float, 3>>(box_length));
+    )
+    RG_CHECK(cudaDeviceSynchronize());
+    std::vector<float> h(blocks);
+    RG_CHECK(static_cast<cudaError_t>(d_rr.down(h.data())));
+    *max_rr = *std::max_element(h.begin(), h.end());
+    return 0;
+}
+
+// binning::update (binning.cpp:176-183): cell index of every slot of the particle array
+int refgpu_compute_cell(const float* position4, size_t array_size, const float cell_length[3], const unsigned ncell[3],
+                        uint32_t* cell)
+{
+    if (array_size % 128 != 0) return static_cast<int>(cudaErrorInvalidValue);
+    dbuf<float4> d_pos(reinterpret_cast<const float4*>(position4), array_size);
+    dbuf<unsigned int> d_cell(array_size);
+    if (!d_pos.p || !d_cell.p) return static_cast<int>(cudaErrorMemoryAllocation);
+    fixed_vector<unsigned int, 3> nc;
+    for (int d = 0; d < 3; ++d) nc[d] = ncell[d];
+    auto& kernel = binning_wrapper<3>::kernel;
+    RG_TRY(
+        kernel.compute_cell.configure(dim3(static_cast<unsigned>(array_size / 128)), dim3(128));
+        kernel.compute_cell(d_pos.p, d_cell.p, vec3<fixed_vector<float, 3>>(cell_length), nc);
+    )
+    RG_CHECK(cudaDeviceSynchronize());
+    return d_cell.down(cell);
+}
+
+// integrators::verlet (verlet.cpp:64-121), double-single arrays: high words [0, A), low words [A, 2A)
+int refgpu_verlet(int do_finalize, int do_integrate, float* position8, float* image4, float* velocity8, const float* force4,
+                  size_t array_size, float timestep, const float box_length[3])
+{
+    typedef integrators::verlet_wrapper<3, dsfloat> wrapper_type;
+    typedef wrapper_type::ptr_type ptr_type;
+    if (array_size % 128 != 0) return static_cast<int>(cudaErrorInvalidValue);
+    dbuf<float4> d_pos(reinterpret_cast<const float4*>(position8), 2 * array_size);
+    dbuf<float4> d_vel(reinterpret_cast<const float4*>(velocity8), 2 * array_size);
+    dbuf<float4> d_img(reinterpret_cast<const float4*>(image4), array_size);
+    dbuf<float4> d_f(reinterpret_cast<const float4*>(force4), array_size);
+    if (!d_pos.p || !d_vel.p || !d_img.p || !d_f.p) return static_cast<int>(cudaErrorMemoryAllocation);
+    ptr_type pos = {d_pos.p, d_pos.p + array_size}, vel = {d_vel.p, d_vel.p + array_size};
+    dim3 const grid(static_cast<unsigned>(array_size / 128)), block(128);
+    RG_TRY(
+        if (do_finalize) {
+            wrapper_type::wrapper.finalize.configure(grid, block);
+            wrapper_type::wrapper.finalize(vel, d_f.p, timestep);
+        }
+        if (do_integrate) {
+            wrapper_type::wrapper.integrate.configure(grid, block);
+            wrapper_type::wrapper.integrate(pos, d_img.p, vel, d_f.p, timestep, vec3<fixed_vector<float, 3>>(box_length));
+        }
+    )
+    RG_CHECK(cudaDeviceSynchronize());
+    int rc;
+    if ((rc = d_pos.down(reinterpret_cast<float4*>(position8)))) return rc;
+    if ((rc = d_vel.down(reinterpret_cast<float4*>(velocity8)))) return rc;
+    return d_img.down(reinterpret_cast<float4*>(image4));
+}
+
+} // extern "C"
+
+namespace {
+
+namespace lj = potentials::pair::lennard_jones_kernel;
+namespace tr = potentials::pair::truncations;
+
+// pair_trunc::compute_ / compute_aux_ (pair_trunc.hpp:217-337): one thread per slot of the particle array (default lists)
+// or nparallel_particles threads per slot (unroll_force_loop)
+template <typename potential_type>
+int launch_force(potential_type const& pot, const float4* pos, cudaTextureObject_t t_r2, float4* force, const unsigned int* nl,
+                 unsigned size, unsigned stride, int layout, float* en_pot, float* stress, unsigned ntype, const float* L,
+                 bool force_zero, float aux_weight, size_t array_size)
+{
+    typedef forces::pair_trunc_wrapper<3, potential_type> wrapper_type;
+    auto& k = wrapper_type::kernel;
+    fixed_vector<float, 3> const box = vec3<fixed_vector<float, 3>>(L);
+    bool const aux = en_pot != nullptr;
+    RG_TRY(
+        if (layout) {
+            size_t const threads = array_size * k.nparallel_particles;
+            auto& f = aux ? k.compute_aux_unroll_force_loop : k.compute_unroll_force_loop;
+            f.configure(dim3(static_cast<unsigned>(threads / 256)), dim3(256));
+            f(pot, pos, t_r2, force, nl, size, en_pot, stress, ntype, ntype, box, force_zero, aux_weight);
+        } else {
+            auto& f = aux ? k.compute_aux : k.compute;
+            f.configure(dim3(static_cast<unsigned>(array_size / 128)), dim3(128));
+            f(pot, pos, t_r2, force, nl, size, stride, en_pot, stress, ntype, ntype, box, force_zero, aux_weight);
+        }
+    )
+    RG_CHECK(cudaDeviceSynchronize());
+    return 0;
+}
+
+} // namespace
+
+// truncation: 0 sharp, 1 shifted, 2 smooth_r4.  Parameter tables [ntype * ntype] as lennard_jones.cpp:60-105 and
+// truncations/{sharp,shifted,smooth_r4}.hpp upload them: (epsilon, sigma2); rr_cut; (rr_cut, en_cut);
+// (r_cut, rr_cut, en_cut); rri_smooth = h^-2 (smooth_r4.hpp:97).
+// force (in/out, array_size float4); en_pot (array_size) and stress (6 * array_size) may both be NULL (no aux).
+extern "C" int refgpu_pair_force(int truncation, unsigned ntype, const float* epsilon, const float* sigma2, const float* r_cut,
+                                 const float* rr_cut, const float* en_cut, float rri_smooth, const float* position4,
+                                 size_t array_size, const uint32_t* g_neighbour, unsigned size, size_t stride, int layout,
+                                 const float box_length[3], int force_zero, float aux_weight, float* force4, float* en_pot,
+                                 float* stress)
+{
+    if (array_size % 256 != 0) return static_cast<int>(cudaErrorInvalidValue);
+    unsigned const np = ntype * ntype;
+    std::vector<float2> h_lj(np), h_sh(np);
+    std::vector<float4> h_sm(np);
+    std::vector<float> h_sp(np);
+    for (unsigned t = 0; t < np; ++t) {
+        h_lj[t] = make_float2(epsilon[t], sigma2[t]);                 // lennard_jones_kernel::EPSILON, SIGMA2
+        h_sm[t] = make_float4(r_cut[t], rr_cut[t], en_cut[t], 0.f);   // smooth_r4_kernel::R_CUT, RR_CUT, EN_CUT
+        h_sh[t] = make_float2(rr_cut[t], en_cut[t]);                  // shifted_kernel::RR_CUT, EN_CUT
+        h_sp[t] = rr_cut[t];
+    }
+    dbuf<float2> d_lj(h_lj.data(), np), d_sh(h_sh.data(), np);
+    dbuf<float4> d_sm(h_sm.data(), np);
+    dbuf<float> d_sp(h_sp.data(), np);
+    size_t const nl_len = static_cast<size_t>(size) * stride;
+    dbuf<float4> d_pos(reinterpret_cast<const float4*>(position4), array_size);
+    dbuf<unsigned int> d_nl(g_neighbour, nl_len);
+    dbuf<float4> d_f(reinterpret_cast<const float4*>(force4), array_size);
+    bool const aux = en_pot != nullptr;
+    dbuf<float> d_en(en_pot, aux ? array_size : 0), d_st(stress, aux ? 6 * array_size : 0);
+    if (!d_pos.p || !d_nl.p || !d_f.p || !d_en.p || !d_st.p) return static_cast<int>(cudaErrorMemoryAllocation);
+    lintex<float2> t_lj(d_lj.p, np), t_sh(d_sh.p, np);
+    lintex<float4> t_sm(d_sm.p, np), t_r2(d_pos.p, array_size);
+    lintex<float> t_sp(d_sp.p, np);
+    lj::lennard_jones const parent(t_lj.t);
+    float* const en = aux ? d_en.p : nullptr;
+    float* const st = aux ? d_st.p : nullptr;
+    unsigned const pitch = static_cast<unsigned>(stride);
+    int rc;
+    if (truncation == 2) {
+        RG_TRY(tr::smooth_r4_wrapper<lj::lennard_jones>::rri_smooth.set(rri_smooth))
+        tr::smooth_r4_kernel::smooth_r4<lj::lennard_jones> pot(parent, t_sm.t);
+        rc = launch_force(pot, d_pos.p, t_r2.t, d_f.p, d_nl.p, size, pitch, layout, en, st, ntype, box_length, force_zero != 0, aux_weight, array_size);
+    } else if (truncation == 1) {
+        tr::shifted_kernel::shifted<lj::lennard_jones> pot(parent, t_sh.t);
+        rc = launch_force(pot, d_pos.p, t_r2.t, d_f.p, d_nl.p, size, pitch, layout, en, st, ntype, box_length, force_zero != 0, aux_weight, array_size);
+    } else {
+        tr::sharp_kernel::sharp<lj::lennard_jones> pot(parent, t_sp.t);
+        rc = launch_force(pot, d_pos.p, t_r2.t, d_f.p, d_nl.p, size, pitch, layout, en, st, ntype, box_length, force_zero != 0, aux_weight, array_size);
+    }
+    if (rc) return rc;
+    if ((rc = d_f.down(reinterpret_cast<float4*>(force4)))) return rc;
+    if (aux) {
+        if ((rc = d_en.down(en_pot))) return rc;
+        if ((rc = d_st.down(stress))) return rc;
+    }
+    return 0;
+}
