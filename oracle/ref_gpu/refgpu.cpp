@@ -11,6 +11,8 @@
 #include <halmd/mdsim/gpu/binning_kernel.hpp>
 #include <halmd/mdsim/gpu/forces/pair_trunc_kernel.hpp>
 #include <halmd/mdsim/gpu/integrators/verlet_kernel.hpp>
+#include <halmd/mdsim/gpu/integrators/verlet_nvt_andersen_kernel.hpp>
+#include <halmd/random/gpu/rand48_kernel.cuh>
 #include <halmd/mdsim/gpu/max_displacement_kernel.hpp>
 #include <halmd/mdsim/gpu/neighbours/from_binning_kernel.hpp>
 #include <halmd/mdsim/gpu/potentials/pair/lennard_jones_kernel.hpp>
@@ -159,6 +161,84 @@ int refgpu_compute_cell(const float* position4, size_t array_size, const float c
     )
     RG_CHECK(cudaDeviceSynchronize());
     return d_cell.down(cell);
+}
+
+// binning::update (binning.cpp:166-221): compute_cell, gen_index, stable sort of (cell, index) — the reference's
+// radix_sort is a stable LSD sort (test/unit/algorithm/radix_sort.cpp compares it with std::stable_sort); it is
+// replaced by std::stable_sort on the host here —, find_cell_offset, assign_cells.  g_cell[ncells * cell_size].
+int refgpu_binning_update(const float* position4, size_t nparticle, size_t array_size, const float cell_length[3],
+                          const unsigned ncell[3], unsigned cell_size, uint32_t* g_cell, int* overcrowded)
+{
+    if (array_size % 128 != 0) return static_cast<int>(cudaErrorInvalidValue);
+    size_t const ncells = static_cast<size_t>(ncell[0]) * ncell[1] * ncell[2];
+    dbuf<float4> d_pos(reinterpret_cast<const float4*>(position4), array_size);
+    dbuf<unsigned int> d_index(array_size), d_perm(array_size), d_offset(ncells), d_cell(ncells * cell_size);
+    dbuf<int> d_ret(1);
+    if (!d_pos.p || !d_index.p || !d_perm.p || !d_offset.p || !d_cell.p || !d_ret.p) return static_cast<int>(cudaErrorMemoryAllocation);
+    fixed_vector<unsigned int, 3> nc;
+    for (int d = 0; d < 3; ++d) nc[d] = ncell[d];
+    auto& kernel = binning_wrapper<3>::kernel;
+    dim3 const grid(static_cast<unsigned>(array_size / 128)), block(128);
+    unsigned const nbox = static_cast<unsigned>(nparticle);
+    RG_TRY(
+        kernel.compute_cell.configure(grid, block);
+        kernel.compute_cell(d_pos.p, d_index.p, vec3<fixed_vector<float, 3>>(cell_length), nc);
+        kernel.gen_index.configure(grid, block);
+        kernel.gen_index(d_perm.p, nbox);
+    )
+    RG_CHECK(cudaDeviceSynchronize());
+    std::vector<unsigned int> h_index(array_size), h_perm(array_size), order(array_size);
+    RG_CHECK(static_cast<cudaError_t>(d_index.down(h_index.data())));
+    RG_CHECK(static_cast<cudaError_t>(d_perm.down(h_perm.data())));
+    for (size_t i = 0; i < array_size; ++i) order[i] = static_cast<unsigned int>(i);
+    std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return h_index[a] < h_index[b]; });
+    std::vector<unsigned int> s_index(array_size), s_perm(array_size);
+    for (size_t i = 0; i < array_size; ++i) { s_index[i] = h_index[order[i]]; s_perm[i] = h_perm[order[i]]; }
+    RG_CHECK(cudaMemcpy(d_index.p, s_index.data(), array_size * sizeof(unsigned int), cudaMemcpyHostToDevice));
+    RG_CHECK(cudaMemcpy(d_perm.p, s_perm.data(), array_size * sizeof(unsigned int), cudaMemcpyHostToDevice));
+    RG_CHECK(cudaMemset(d_offset.p, 0xFF, ncells * sizeof(unsigned int)));
+    RG_CHECK(cudaMemset(d_ret.p, 0, sizeof(int)));
+    RG_TRY(
+        kernel.find_cell_offset.configure(grid, block);
+        kernel.find_cell_offset(d_index.p, d_offset.p, nbox);
+        kernel.assign_cells.configure(dim3(static_cast<unsigned>(ncells)), dim3(cell_size));
+        kernel.assign_cells(d_ret.p, d_index.p, d_offset.p, d_perm.p, d_cell.p, nbox, cell_size);
+    )
+    RG_CHECK(cudaDeviceSynchronize());
+    int ret = 0;
+    RG_CHECK(static_cast<cudaError_t>(d_ret.down(&ret)));
+    if (overcrowded) *overcrowded = ret;
+    return d_cell.down(g_cell);
+}
+
+// integrators::verlet_nvt_andersen::finalize (verlet_nvt_andersen.cpp:109-138): launched with the execution dimensions
+// of the random number generator; rand48 state (ushort3 per RNG thread) and leapfrog constants a, c (16-bit words, low
+// word first) are passed in and the advanced state is returned.
+int refgpu_andersen_finalize(float* velocity8, const float* force4, size_t nparticle, size_t array_size, float timestep,
+                             float sqrt_temperature, float coll_prob, unsigned blocks, unsigned threads,
+                             const uint16_t a[3], const uint16_t c[3], uint16_t* state)
+{
+    typedef integrators::verlet_nvt_andersen_wrapper<3, dsfloat, random::gpu::rand48_rng> wrapper_type;
+    typedef wrapper_type::ptr_type ptr_type;
+    size_t const nthread = static_cast<size_t>(blocks) * threads;
+    dbuf<float4> d_vel(reinterpret_cast<const float4*>(velocity8), 2 * array_size);
+    dbuf<float4> d_f(reinterpret_cast<const float4*>(force4), array_size);
+    dbuf<ushort3> d_state(reinterpret_cast<const ushort3*>(state), nthread);
+    if (!d_vel.p || !d_f.p || !d_state.p) return static_cast<int>(cudaErrorMemoryAllocation);
+    random::gpu::rand48_rng rng;
+    rng.a = make_uint48(a[0], a[1], a[2]);
+    rng.c = make_uint48(c[0], c[1], c[2]);
+    rng.g_state = d_state.p;
+    ptr_type vel = {d_vel.p, d_vel.p + array_size};
+    RG_TRY(
+        wrapper_type::kernel.finalize.configure(dim3(blocks), dim3(threads));
+        wrapper_type::kernel.finalize(vel, d_f.p, timestep, sqrt_temperature, coll_prob, static_cast<unsigned>(nparticle),
+                                      static_cast<unsigned>(array_size), rng);
+    )
+    RG_CHECK(cudaDeviceSynchronize());
+    int rc;
+    if ((rc = d_vel.down(reinterpret_cast<float4*>(velocity8)))) return rc;
+    return d_state.down(reinterpret_cast<ushort3*>(state));
 }
 
 // integrators::verlet (verlet.cpp:64-121), double-single arrays: high words [0, A), low words [A, 2A)
