@@ -32,6 +32,18 @@ class LjParams(C.Structure):
     ]
 
 
+MAX_WALLS, MAX_WALL_SPECIES = 8, 4
+
+
+class PlanarWall(C.Structure):
+    _fields_ = [
+        ("nwall", C.c_uint), ("nspecies", C.c_uint), ("smoothing", C.c_float),
+        ("surface_normal", (C.c_float * 3) * MAX_WALLS), ("offset", C.c_float * MAX_WALLS),
+        ("epsilon", C.c_float * (MAX_WALL_SPECIES * MAX_WALLS)), ("sigma", C.c_float * (MAX_WALL_SPECIES * MAX_WALLS)),
+        ("wetting", C.c_float * (MAX_WALL_SPECIES * MAX_WALLS)), ("cutoff", C.c_float * (MAX_WALL_SPECIES * MAX_WALLS)),
+    ]
+
+
 class Rand48(C.Structure):
     _fields_ = [("blocks", C.c_uint), ("threads", C.c_uint), ("a", C.c_uint16 * 3), ("c", C.c_uint16 * 3)]
 
@@ -75,6 +87,8 @@ _protos = {
     "hx_potential_lj_init": (C.c_int, [C.POINTER(LjParams), C.c_uint, C.c_uint, F3, F3, C.c_int, F3, C.c_float]),
     "hx_pair_force": (C.c_int, [C.POINTER(LjParams), P, P, P, C.c_uint, SZ, C.c_int, SZ, F3, C.c_int,
                                 C.c_float, P, P, P, SZ, P]),
+    "hx_planar_wall_init": (C.c_int, [C.POINTER(PlanarWall), C.c_uint, C.c_uint, F3, F3, F3, F3, F3, F3, C.c_float]),
+    "hx_external_planar_wall": (C.c_int, [C.POINTER(PlanarWall), P, SZ, F3, C.c_int, P, P, P, SZ, P, P]),
     "hx_pair_force_guarded": (C.c_int, [C.POINTER(LjParams), P, P, P, C.c_uint, SZ, C.c_int, SZ, F3, C.c_int,
                                         C.c_float, P, P, P, SZ, P, C.c_float, P]),
     "hx_pair_force_set_lanes": (C.c_int, [C.c_int]),
@@ -143,6 +157,7 @@ _module_protos = {
     "hxm_force_pair_trunc_create": (C.c_int, [P, P, D3, P, C.c_float, PP]),
     "hxm_force_destroy": (None, [P]),
     "hxm_force_apply": (C.c_int, [P]),
+    "hxm_force_add_planar_wall": (C.c_int, [P, C.POINTER(PlanarWall)]),
     "hxm_integrator_verlet_create": (C.c_int, [P, P, D3, C.c_double, PP]),
     "hxm_integrator_andersen_create": (C.c_int, [P, P, D3, C.c_double, C.c_double, C.c_double, C.c_uint, PP]),
     "hxm_integrator_destroy": (None, [P]),

@@ -288,6 +288,61 @@ class _pair_force(_Handle):
         check(lib.hxm_force_apply(self._h), "force.apply")
 
 
+# ---- mdsim.potentials.external.planar_wall / mdsim.forces.external ---------------------------------------------------------
+class _planar_wall:
+    """lua/halmd/mdsim/potentials/external/planar_wall.lua.in: offset[nwall], surface_normal[nwall][3] (or one normal
+    for all walls), epsilon / sigma / wetting / cutoff as numbers or [nwall][species] matrices, smoothing, species."""
+
+    def __init__(self, offset=None, surface_normal=None, epsilon=None, sigma=None, wetting=None, cutoff=None,
+                 smoothing=None, species=None, memory=None, label=None):
+        for name, v in (("offset", offset), ("surface_normal", surface_normal), ("epsilon", epsilon), ("sigma", sigma),
+                        ("wetting", wetting), ("cutoff", cutoff), ("smoothing", smoothing), ("species", species)):
+            if v is None:
+                raise ValueError(f"missing argument '{name}'")
+        offset = np.atleast_1d(np.asarray(offset, dtype=np.float32))
+        nwall, species = len(offset), int(species)
+        normal = np.asarray(surface_normal, dtype=np.float32)
+        if normal.ndim == 1:
+            normal = np.tile(normal, (nwall, 1))
+        if normal.shape != (nwall, 3):
+            raise ValueError("bad argument 'surface_normal'")
+
+        def matrix(v, name):
+            m = np.asarray(v, dtype=np.float32)
+            if m.ndim == 0:
+                m = np.full((nwall, species), float(v), dtype=np.float32)
+            if m.shape != (nwall, species):
+                raise ValueError(f"mismatching shape of argument '{name}'")
+            return np.ascontiguousarray(m)
+
+        self.offset, self.surface_normal = offset, normal
+        self.epsilon, self.sigma = matrix(epsilon, "epsilon"), matrix(sigma, "sigma")
+        self.wetting, self.cutoff = matrix(wetting, "wetting"), matrix(cutoff, "cutoff")
+        self.smoothing, self.species, self.nwall = float(smoothing), species, nwall
+        self.params = hx.PlanarWall()
+        check(lib.hx_planar_wall_init(C.byref(self.params), nwall, species, hx.farr(offset), hx.farr(normal.reshape(-1)),
+                                      hx.farr(self.epsilon.reshape(-1)), hx.farr(self.sigma.reshape(-1)),
+                                      hx.farr(self.wetting.reshape(-1)), hx.farr(self.cutoff.reshape(-1)), self.smoothing),
+              "potentials.external.planar_wall")
+
+
+class _external_force:
+    """lua/halmd/mdsim/forces/external.lua.in.  The contribution is evaluated after the particle's pair force (which
+    must have been constructed before), adding to the same force array."""
+
+    def __init__(self, box=None, particle=None, potential=None):
+        if not isinstance(potential, _planar_wall):
+            raise HxError("forces.external: only potentials.external.planar_wall is supported")
+        pair = getattr(particle, "_force", None)
+        if pair is None:
+            raise HxError("forces.external: construct mdsim.forces.pair{particle=...} first")
+        self.box, self.particle, self.potential, self.pair = box, particle, potential, pair
+        check(lib.hxm_force_add_planar_wall(pair._h, C.byref(potential.params)), "mdsim.forces.external")
+
+    def apply(self):
+        self.pair.apply()
+
+
 # ---- integrators -----------------------------------------------------------------------------------------------------------
 class _integrator(_Handle):
     _destroy = "hxm_integrator_destroy"
@@ -533,8 +588,8 @@ def _pair(**kw):
 
 mdsim = _NS(
     box=box, particle=particle, binning=binning, neighbour=neighbour, core=core,
-    potentials=_NS(pair=_NS(lennard_jones=_lennard_jones)),
-    forces=_NS(pair=_pair),
+    potentials=_NS(pair=_NS(lennard_jones=_lennard_jones), external=_NS(planar_wall=_planar_wall)),
+    forces=_NS(pair=_pair, external=_external_force),
     integrators=_NS(verlet=_verlet, verlet_nvt_andersen=_verlet_nvt_andersen),
 )
 

@@ -288,6 +288,8 @@ struct hxm_force {
     hxm_neighbour* neighbour = nullptr;
     float Lf[3];
     float aux_weight = 1;
+    // further contributions to the same force array (particle.on_force slots after the first: force_zero = false)
+    std::vector<hx_planar_wall> walls;      // mdsim.forces.external with potentials.external.planar_wall
 
     // weight / 2 for particle1 == particle2 (pair_trunc.hpp:291-294)
     float weight() const { return aux_weight / 2; }
@@ -298,14 +300,21 @@ struct hxm_force {
         hx_float4* pos = reinterpret_cast<hx_float4*>(p->pos);
         int const layout = neighbour->layout | (p->reduced ? HX_FORCE_POSITIONS_REDUCED : 0);
         if (ctl) {
-            return hx_pair_force_guarded(&potential->p, pos, pos, neighbour->g_neighbour, neighbour->size,
-                                         neighbour->stride, layout, p->n, Lf, 1, weight(),
-                                         reinterpret_cast<hx_float4*>(p->force), aux ? p->en_pot : nullptr,
-                                         aux ? p->stress : nullptr, p->A, ctl, skin_half, p->st);
+            HXM_TRY(hx_pair_force_guarded(&potential->p, pos, pos, neighbour->g_neighbour, neighbour->size,
+                                          neighbour->stride, layout, p->n, Lf, 1, weight(),
+                                          reinterpret_cast<hx_float4*>(p->force), aux ? p->en_pot : nullptr,
+                                          aux ? p->stress : nullptr, p->A, ctl, skin_half, p->st));
+        } else {
+            HXM_TRY(hx_pair_force(&potential->p, pos, pos, neighbour->g_neighbour, neighbour->size, neighbour->stride,
+                                  layout, p->n, Lf, 1, weight(), reinterpret_cast<hx_float4*>(p->force),
+                                  aux ? p->en_pot : nullptr, aux ? p->stress : nullptr, p->A, p->st));
         }
-        return hx_pair_force(&potential->p, pos, pos, neighbour->g_neighbour, neighbour->size, neighbour->stride,
-                             layout, p->n, Lf, 1, weight(), reinterpret_cast<hx_float4*>(p->force),
-                             aux ? p->en_pot : nullptr, aux ? p->stress : nullptr, p->A, p->st);
+        // (a halted chunk: the guarded pair kernel raised the flag before this kernel reads it, in stream order)
+        for (hx_planar_wall const& w : walls) {
+            HXM_TRY(hx_external_planar_wall(&w, pos, p->n, Lf, 0, reinterpret_cast<hx_float4*>(p->force),
+                                            aux ? p->en_pot : nullptr, aux ? p->stress : nullptr, p->A, ctl, p->st));
+        }
+        return 0;
     }
 
     // particle::update_force_ (particle.cpp:221-253) + pair_trunc::check_cache/apply (pair_trunc.hpp:175-215)
@@ -991,6 +1000,20 @@ int hxm_force_pair_trunc_create(hxm_potential* potential, hxm_particle* particle
 }
 
 void hxm_force_destroy(hxm_force* f) { delete f; }
+
+int hxm_force_add_planar_wall(hxm_force* f, const hx_planar_wall* wall)
+{
+    if (!f || !wall || wall->nwall == 0 || wall->nwall > HX_MAX_WALLS || wall->nspecies < f->particle->nspecies
+        || wall->nspecies > HX_MAX_WALL_SPECIES) {
+        set_error("forces.external: invalid planar_wall potential (nspecies %u, particle has %u)", wall ? wall->nspecies : 0,
+                  f ? f->particle->nspecies : 0);
+        return HX_E_INVALID;
+    }
+    f->walls.push_back(*wall);
+    f->particle->force_pos_ver = 0;      // force cache is stale
+    f->particle->aux_valid = false;
+    return 0;
+}
 
 int hxm_force_apply(hxm_force* f)
 {

@@ -177,6 +177,33 @@ int hx_pair_force_set_lanes(int lanes);
 /* tuning knob: packed f32x2 arithmetic in the ROW kernel (default 1); 0 selects the scalar instruction stream */
 int hx_pair_force_set_packed(int enable);
 
+/* ---- f1: external one-body force, planar Lennard-Jones 9-3 walls -----------------------------------------------
+ * halmd/mdsim/gpu/forces/external.hpp:120-190, external_kernel.cuh:49-103,
+ * halmd/mdsim/gpu/potentials/external/planar_wall.cpp:40-112, planar_wall_kernel.cu:43-105.
+ * Parameter tables are indexed [species * nwall + wall] like the reference's parameter texture; surface normals are
+ * normalised by hx_planar_wall_init (planar_wall.cpp:83-86).  The kernel adds to force / en_pot when force_zero == 0
+ * (external_kernel.cuh:78-99: the stress contribution of the wall is not implemented in the reference — zero).
+ * ctl_dev (may be NULL): returns at once when the control block is halted (chunked stepping). */
+#define HX_MAX_WALLS 8
+#define HX_MAX_WALL_SPECIES 4
+typedef struct hx_planar_wall {
+    unsigned nwall, nspecies;
+    float smoothing;
+    float surface_normal[HX_MAX_WALLS][3];
+    float offset[HX_MAX_WALLS];
+    float epsilon[HX_MAX_WALL_SPECIES * HX_MAX_WALLS];
+    float sigma[HX_MAX_WALL_SPECIES * HX_MAX_WALLS];
+    float wetting[HX_MAX_WALL_SPECIES * HX_MAX_WALLS];
+    float cutoff[HX_MAX_WALL_SPECIES * HX_MAX_WALLS];
+} hx_planar_wall;
+/* epsilon, sigma, wetting, cutoff: [nwall][nspecies] row-major as in the Lua module (planar_wall.lua.in) */
+int hx_planar_wall_init(hx_planar_wall* w, unsigned nwall, unsigned nspecies, const float* offset,
+                        const float* surface_normal /* [nwall][3] */, const float* epsilon, const float* sigma,
+                        const float* wetting, const float* cutoff, float smoothing);
+int hx_external_planar_wall(const hx_planar_wall* wall, const hx_float4* position_hi_dev, size_t nparticle,
+                            const float box_length[3], int force_zero, hx_float4* force_dev, float* en_pot_dev,
+                            float* stress_dev, size_t stress_stride, const uint32_t* ctl_dev, void* stream);
+
 /* ---- a12: velocity-Verlet in double-single arithmetic -------------------------------------
  * halmd/mdsim/gpu/integrators/verlet.cpp:64-121, verlet_kernel.cu:37-98,
  * halmd/numeric/mp/dsfun.hpp:142-207. */

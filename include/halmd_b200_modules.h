@@ -106,6 +106,10 @@ int hxm_force_pair_trunc_create(hxm_potential* potential, hxm_particle* particle
 void hxm_force_destroy(hxm_force* f);
 /* force:apply() through particle->force() laziness: recomputes only if positions changed (pair_trunc.hpp:175-215) */
 int hxm_force_apply(hxm_force* f);
+/* mdsim.forces.external{particle, box, potential = potentials.external.planar_wall{...}} (external.lua.in,
+ * halmd/mdsim/gpu/forces/external.hpp:120-190): a further contribution to the particle's force array, evaluated
+ * after the pair force of `f` with force_zero = false (particle.cpp:221-253). */
+int hxm_force_add_planar_wall(hxm_force* f, const hx_planar_wall* wall);
 
 /* ---- integrators ---------------------------------------------------------------------------------------------------- */
 int hxm_integrator_verlet_create(hxm_particle* particle, hxm_force* force, const double box_length[3], double timestep,

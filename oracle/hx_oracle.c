@@ -724,3 +724,62 @@ void oracle_thermodynamics(const f4* vel, const float* en_pot, const float* stre
         if (stress) out[6] += (double)stress[i] + (double)stress[stress_stride + i] + (double)stress[2 * stress_stride + i];
     }
 }
+
+/* ---- external one-body force, planar walls --------------------------------------------------------------------
+ * halmd/mdsim/gpu/forces/external_kernel.cuh:49-103 + potentials/external/planar_wall_kernel.cu:43-105 in float
+ * with IEEE division (the device build divides approximately).  Tables indexed [species * nwall + wall]. */
+typedef struct {
+    unsigned nwall, nspecies;
+    float smoothing;
+    float surface_normal[8][3];
+    float offset[8];
+    float epsilon[32], sigma[32], wetting[32], cutoff[32];
+} planar_wall_t;
+
+void oracle_planar_wall(const planar_wall_t* w, const f4* pos, size_t n, const float L[3], int force_zero, f4* force,
+                        float* en_pot_out, float* stress, size_t stress_stride)
+{
+    for (size_t i = 0; i < n; ++i) {
+        float r[3] = {pos[i].x, pos[i].y, pos[i].z};
+        unsigned species;
+        memcpy(&species, &pos[i].w, 4);
+        for (int d = 0; d < 3; ++d) r[d] = fmaf(-rintf(r[d] / L[d]), L[d], r[d]);      /* reduce_periodic */
+        float en_pot = 0, f[3] = {0, 0, 0};
+        for (unsigned k = 0; k < w->nwall; ++k) {
+            const float* nrm = w->surface_normal[k];
+            /* inner_prod in the order nvcc emits for the reference kernel: y*ny, then x, then z (fused) */
+            float d = fmaf(r[2], nrm[2], fmaf(r[0], nrm[0], r[1] * nrm[1])) - w->offset[k];
+            unsigned t = species * w->nwall + k;
+            float epsilon = w->epsilon[t], sigma = w->sigma[t], wet = w->wetting[t], cutoff = w->cutoff[t];
+            if (fabsf(d) >= cutoff) continue;
+            float sc = sigma / cutoff;
+            float dc3i = sc * sc * sc;
+            float dc6i = (2.f / 15) * dc3i * dc3i;
+            float en_cut = epsilon * dc3i * (dc6i - wet);
+            float sd = sigma / d;
+            float d3i = sd * sd * sd;
+            float d6i = (2.f / 15) * d3i * d3i;
+            float eps_d3i = (d > 0 ? 1.f : -1.f) * epsilon * d3i;
+            float en_sub = eps_d3i * (d6i - wet) - en_cut;
+            float fval = 3.f * eps_d3i * (3.f * d6i - wet) / d;
+            float dd = (fabsf(d) - cutoff) / w->smoothing;
+            float x2 = dd * dd, x4 = x2 * x2;
+            float x4i = 1.f / (1.f + x4);
+            float h0 = x4 * x4i;
+            float h1 = 4.f * dd * x2 * x4i * x4i;
+            fval = h0 * fval - h1 * en_sub / w->smoothing;
+            en_sub = h0 * en_sub;
+            for (int c = 0; c < 3; ++c) f[c] = fmaf(fval, nrm[c], f[c]);
+            en_pot += en_sub;
+        }
+        if (!force_zero) {
+            f[0] += force[i].x; f[1] += force[i].y; f[2] += force[i].z;
+        }
+        force[i].x = f[0]; force[i].y = f[1]; force[i].z = f[2]; force[i].w = 0;
+        if (en_pot_out) {
+            if (!force_zero) en_pot += en_pot_out[i];
+            else for (int c = 0; c < 6; ++c) stress[c * stress_stride + i] = 0;
+            en_pot_out[i] = en_pot;
+        }
+    }
+}

@@ -9,7 +9,9 @@
 // Every entry point takes HOST arrays and is synchronous.  Return value: 0 or a cudaError_t.
 #include <halmd/config.hpp>
 #include <halmd/mdsim/gpu/binning_kernel.hpp>
+#include <halmd/mdsim/gpu/forces/external_kernel.hpp>
 #include <halmd/mdsim/gpu/forces/pair_trunc_kernel.hpp>
+#include <halmd/mdsim/gpu/potentials/external/planar_wall_kernel.hpp>
 #include <halmd/mdsim/gpu/integrators/verlet_kernel.hpp>
 #include <halmd/mdsim/gpu/integrators/verlet_nvt_andersen_kernel.hpp>
 #include <halmd/random/gpu/rand48_kernel.cuh>
@@ -359,6 +361,46 @@ extern "C" int refgpu_pair_force(int truncation, unsigned ntype, const float* ep
         rc = launch_force(pot, d_pos.p, t_r2.t, d_f.p, d_nl.p, size, pitch, layout, en, st, ntype, box_length, force_zero != 0, aux_weight, array_size);
     }
     if (rc) return rc;
+    if ((rc = d_f.down(reinterpret_cast<float4*>(force4)))) return rc;
+    if (aux) {
+        if ((rc = d_en.down(en_pot))) return rc;
+        if ((rc = d_st.down(stress))) return rc;
+    }
+    return 0;
+}
+
+// forces::external<3, float, planar_wall> (external.hpp:120-190) with potentials::external::planar_wall
+// (planar_wall.cpp:40-112): geometry texture (normal, offset), potential texture [species * nwall + wall] =
+// (epsilon, sigma, wetting, cutoff), symbols nwall and smoothing; one thread per slot of the particle array.
+// Normals must be normalised by the caller (the host class does it before the upload).
+extern "C" int refgpu_planar_wall(unsigned nwall, unsigned nspecies, const float* normal_offset4 /* [nwall] float4 */,
+                                  const float* potential4 /* [nspecies * nwall] float4 */, float smoothing,
+                                  const float* position4, size_t array_size, const float box_length[3], int force_zero,
+                                  float* force4, float* en_pot, float* stress)
+{
+    using namespace potentials::external;
+    typedef planar_wall_kernel::planar_wall<3> potential_type;
+    typedef forces::external_wrapper<3, potential_type> wrapper_type;
+    if (array_size % 128 != 0) return static_cast<int>(cudaErrorInvalidValue);
+    dbuf<float4> d_geo(reinterpret_cast<const float4*>(normal_offset4), nwall);
+    dbuf<float4> d_pot(reinterpret_cast<const float4*>(potential4), nspecies * nwall);
+    dbuf<float4> d_pos(reinterpret_cast<const float4*>(position4), array_size);
+    dbuf<float4> d_f(reinterpret_cast<const float4*>(force4), array_size);
+    bool const aux = en_pot != nullptr;
+    dbuf<float> d_en(en_pot, aux ? array_size : 0), d_st(stress, aux ? 6 * array_size : 0);
+    if (!d_geo.p || !d_pot.p || !d_pos.p || !d_f.p || !d_en.p || !d_st.p) return static_cast<int>(cudaErrorMemoryAllocation);
+    lintex<float4> t_geo(d_geo.p, nwall), t_pot(d_pot.p, nspecies * nwall);
+    RG_TRY(
+        planar_wall_wrapper::nwall.set(static_cast<int>(nwall));
+        planar_wall_wrapper::smoothing.set(smoothing);
+        potential_type pot(t_geo.t, t_pot.t);
+        auto& f = aux ? wrapper_type::kernel.compute_aux : wrapper_type::kernel.compute;
+        f.configure(dim3(static_cast<unsigned>(array_size / 128)), dim3(128));
+        f(pot, d_pos.p, d_f.p, aux ? d_en.p : nullptr, aux ? d_st.p : nullptr, vec3<fixed_vector<float, 3>>(box_length),
+          force_zero != 0);
+    )
+    RG_CHECK(cudaDeviceSynchronize());
+    int rc;
     if ((rc = d_f.down(reinterpret_cast<float4*>(force4)))) return rc;
     if (aux) {
         if ((rc = d_en.down(en_pot))) return rc;

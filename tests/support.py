@@ -68,6 +68,62 @@ class OLjParams(C.Structure):
     ]
 
 
+class OPlanarWall(C.Structure):
+    _fields_ = [
+        ("nwall", C.c_uint), ("nspecies", C.c_uint), ("smoothing", C.c_float),
+        ("surface_normal", (C.c_float * 3) * 8), ("offset", C.c_float * 8),
+        ("epsilon", C.c_float * 32), ("sigma", C.c_float * 32), ("wetting", C.c_float * 32), ("cutoff", C.c_float * 32),
+    ]
+
+
+# parameters and test positions of the reference's unit test (test/unit/mdsim/potentials/external/planar_wall.cpp:85-147)
+REF_WALL = dict(
+    offset=[-5.0, 5.0, 10.0], surface_normal=[[1, 0, 0], [1, -1, 0], [-1, 0, 2]],
+    cutoff=[[1.0, 2.0], [10.0, 10.0], [1e2, 1e2]], epsilon=[[1.0, 0.5], [2.0, 0.0], [0.0, 1.0]],
+    sigma=[[1.0, 2.0], [3.0, 1.0], [2.0, 1.0]], wetting=[[0.4, 0.0], [-1.0, 1.0], [0.0, 2.0]], smoothing=0.01,
+)
+REF_WALL_POSITIONS = [[0, 0, 0], [5, 0, 1], [-4, 0, 2], [-5.7, 0, 3], [0, -3, 4], [-5.2, -8, 5], [0, 0, 20]]
+
+
+def make_oracle_wall(offset, surface_normal, epsilon, sigma, wetting, cutoff, smoothing):
+    """OPlanarWall filled like planar_wall.cpp:83-112 (normalised normals, tables [species * nwall + wall])."""
+    w = OPlanarWall()
+    eps = np.asarray(epsilon, dtype=np.float32)
+    nwall, nspecies = eps.shape
+    w.nwall, w.nspecies, w.smoothing = nwall, nspecies, smoothing
+    for i in range(nwall):
+        n = np.asarray(surface_normal[i], dtype=np.float32)
+        n = n / np.sqrt(np.float32(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]))
+        for d in range(3):
+            w.surface_normal[i][d] = n[d]
+        w.offset[i] = offset[i]
+        for j in range(nspecies):
+            w.epsilon[j * nwall + i] = epsilon[i][j]
+            w.sigma[j * nwall + i] = sigma[i][j]
+            w.wetting[j * nwall + i] = wetting[i][j]
+            w.cutoff[j * nwall + i] = cutoff[i][j]
+    return w
+
+
+def reference_test_wall(r, normal, offset, epsilon, sigma, wetting, cutoff, smoothing):
+    """compute_wall of the reference's unit test (planar_wall.cpp:48-80), in double precision."""
+    normal = np.asarray(normal, dtype=np.float64)
+    d = float(np.dot(r, normal) - offset)
+    sign = 1.0 if d > 0 else -1.0
+    d = abs(d)
+    if d > cutoff:
+        return np.zeros(3), 0.0
+    fval = 3 * sign * epsilon / sigma * ((2. / 5) * (sigma / d) ** 10 - wetting * (sigma / d) ** 4)
+    en = epsilon * ((2. / 15) * (sigma / d) ** 9 - wetting * (sigma / d) ** 3)
+    en -= epsilon * ((2. / 15) * (sigma / cutoff) ** 9 - wetting * (sigma / cutoff) ** 3)
+    xi = (d - cutoff) / smoothing
+    w = xi ** 4 / (1 + xi ** 4)
+    w1 = 4 * xi ** 3 / (1 + xi ** 4) ** 2
+    fval = fval * w - w1 * en / smoothing
+    en *= w
+    return fval * normal, en
+
+
 class ORand48(C.Structure):
     _fields_ = [("blocks", C.c_uint), ("threads", C.c_uint), ("a", C.c_uint16 * 3), ("c", C.c_uint16 * 3)]
 

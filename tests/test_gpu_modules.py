@@ -370,6 +370,70 @@ def test_run_sampling_matches_manual_sampling(api):
     assert np.array_equal(res[0]["mean"], res[1]["mean"])
 
 
+def slit_pore(n=4000, D=12.0, seed=5, wall=True, timestep=0.002):
+    """examples/definitions/slit_pore.lua:51-67 scaled down: LJ fluid between two planar walls with normals -+x at
+    x = +-(D + 1) / 2, periodic in y and z."""
+    from halmd_b200 import mdsim
+    rng = np.random.default_rng(seed)
+    Lx = D + 10.0
+    Ly = (n / 0.6 / D) ** 0.5
+    box = mdsim.box(length=[Lx, Ly, Ly])
+    p = mdsim.particle(dimension=3, particles=n, species=1)
+    ext = np.array([D - 2.0, Ly, Ly])
+    a = (np.prod(ext) / n) ** (1 / 3)                      # grid with near-equal spacing in the slab |x| < D/2 - 1
+    mx = max(int(ext[0] / a), 1)
+    my = int(np.ceil(np.sqrt(n / mx)))
+    g = np.stack(np.meshgrid(np.arange(mx), np.arange(my), np.arange(my), indexing="ij"), -1).reshape(-1, 3)
+    assert len(g) >= n
+    g = g[rng.permutation(len(g))[:n]].astype(np.float64)
+    p.set("position", ((g + 0.5) / np.array([mx, my, my]) * ext - 0.5 * ext).astype(np.float32))
+    v = rng.normal(scale=0.9, size=(n, 3))
+    p.set("velocity_ds", v - v.mean(axis=0))
+    pot = mdsim.potentials.pair.lennard_jones().truncate("smooth_r4", cutoff=2.5, h=0.005)
+    force = mdsim.forces.pair(box=box, particle=p, potential=pot)
+    integ = mdsim.integrators.verlet_nvt_andersen(box=box, particle=p, timestep=timestep, temperature=0.9, rate=5.0, seed=3)
+    core = mdsim.core.get()
+    e_pair = core.thermodynamics()["potential_energy"]
+    if wall:
+        w = mdsim.potentials.external.planar_wall(offset=[-(D + 1) / 2] * 2, surface_normal=[[-1, 0, 0], [1, 0, 0]], epsilon=1.0,
+                                                 sigma=1.0, wetting=1.0, cutoff=2.5, smoothing=0.005, species=1)
+        mdsim.forces.external(box=box, particle=p, potential=w)
+    return box, p, force, integ, e_pair
+
+
+def test_slit_pore_external_wall(api):
+    """mdsim.forces.external + potentials.external.planar_wall on top of the pair force: the wall term enters the
+    potential energy, the walls confine the fluid during an Andersen melt, NVE conserves the total energy with the
+    extra force kernel in the chunked step loop, and chunked stepping stays bit-identical to single steps."""
+    from halmd_b200 import mdsim
+    D = 12.0
+    box, p, force, integ, e_pair = slit_pore(D=D)
+    core = mdsim.core.get()
+    e_both = core.thermodynamics()["potential_energy"]
+    assert e_both != e_pair and abs(e_both - e_pair) < 5.0              # wall energy per particle is O(0.1)
+    core.run(1500)
+    assert np.abs(p.get("position")[:, 0]).max() < (D + 1) / 2          # nobody crossed a wall plane
+    mdsim.integrators.verlet(box=box, particle=p, timestep=0.001)
+    core = mdsim.core.get()
+    e0 = core.thermodynamics()["internal_energy"]
+    core.run(2000)
+    e1 = core.thermodynamics()["internal_energy"]
+    assert abs(e1 - e0) < 2e-4 * abs(e0), (e0, e1)
+    assert np.abs(p.get("position")[:, 0]).max() < (D + 1) / 2
+    # chunked == single steps (Andersen melt, 60 steps)
+    states = []
+    for single in (False, True):
+        box, p, force, integ, _ = slit_pore(D=D, seed=6)
+        core = mdsim.core.get()
+        if single:
+            for _ in range(60):
+                core.run(1)
+        else:
+            core.run(60)
+        states.append(state_bytes(p))
+    assert states[0] == states[1]
+
+
 def test_api_errors(api):
     halmd_b200, simulation = api
     from halmd_b200 import mdsim, HxError

@@ -109,3 +109,36 @@ def test_lj_init_tables(oracle):
         assert p.rr_cut[i] == np.float32(p.r_cut[i]) * np.float32(p.r_cut[i])
         u = 4 * eps[i] * ((1 / 2.5) ** 12 - (1 / 2.5) ** 6)
         assert abs(p.en_cut[i] - u) < 1e-6 * abs(u)
+
+
+def test_planar_wall_oracle_against_reference_test_formula(oracle):
+    """The reference's own unit test (test/unit/mdsim/potentials/external/planar_wall.cpp:149-201): three walls, a
+    binary mixture, seven test positions, force and energy against the closed formula of that test.  The reference
+    checks its float GPU path to 10 float epsilon; the wall-2 / species-0 entry has cutoff 10 and smoothing 0.01, where
+    float rounding of (|d| - cutoff) / smoothing is amplified, hence the absolute term.  The formula is evaluated at the
+    float-rounded positions the kernel sees."""
+    w = support.make_oracle_wall(**support.REF_WALL)
+    L = np.array([100.0, 100.0, 100.0])
+    for species in range(2):
+        pos = np.zeros((len(support.REF_WALL_POSITIONS), 4), dtype=np.float32)
+        pos[:, :3] = support.REF_WALL_POSITIONS
+        pos[:, 3] = np.array([species] * len(pos), dtype=np.uint32).view(np.float32)
+        f = np.zeros_like(pos)
+        e = np.zeros(len(pos), dtype=np.float32)
+        st = np.ones(6 * len(pos), dtype=np.float32)
+        oracle.oracle_planar_wall(C.byref(w), support.ptr(pos), C.c_size_t(len(pos)), support.f3(L), 1, support.ptr(f),
+                                  support.ptr(e), support.ptr(st), C.c_size_t(len(pos)))
+        assert np.all(st == 0)
+        for k, r in enumerate(support.REF_WALL_POSITIONS):
+            f2, e2 = np.zeros(3), 0.0
+            for i in range(3):
+                n = np.asarray(support.REF_WALL["surface_normal"][i], dtype=np.float64)
+                fi, ei = support.reference_test_wall(pos[k, :3].astype(np.float64), n / np.linalg.norm(n),
+                                                     support.REF_WALL["offset"][i], support.REF_WALL["epsilon"][i][species],
+                                                     support.REF_WALL["sigma"][i][species], support.REF_WALL["wetting"][i][species],
+                                                     support.REF_WALL["cutoff"][i][species], support.REF_WALL["smoothing"])
+                f2 += fi
+                e2 += ei
+            tol = 10 * 1.1920929e-07
+            assert np.all(np.abs(f[k, :3] - f2) <= tol * np.abs(f2).max() + 2e-6 * abs(e2) + 1e-12), (species, k, f[k, :3], f2)
+            assert abs(e[k] - e2) <= tol * abs(e2) + 1e-9, (species, k, e[k], e2)
