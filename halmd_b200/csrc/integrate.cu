@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(128) k_verlet(float4* __restrict__ pos, float4
                                                unsigned n, unsigned nproc, unsigned A, float dt, vec3 L, vec3 invL,
                                                const float4* __restrict__ r0, unsigned* __restrict__ ctl)
 {
+    pdl_wait();
+    pdl_launch();
     // All loads of the step are issued before the halted flag is tested and before any arithmetic: one memory
     // round trip per thread instead of four dependent ones (the kernel is latency-bound at 256 k particles).
     unsigned const i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -291,9 +293,9 @@ static int verlet_launch(bool fin, bool integ, hx_float4* pos, hx_float4* image,
     const float4* f = reinterpret_cast<const float4*>(force);
     const float4* q = reinterpret_cast<const float4*>(r0);
     unsigned nn = static_cast<unsigned>(n), AA = static_cast<unsigned>(A), np = static_cast<unsigned>(nproc);
-    if (fin && integ) k_verlet<true, true><<<grid, block, 0, st>>>(p, im, v, f, nn, np, AA, dt, Lv, iLv, q, ctl);
-    else if (integ) k_verlet<false, true><<<grid, block, 0, st>>>(p, im, v, f, nn, np, AA, dt, Lv, iLv, q, ctl);
-    else k_verlet<true, false><<<grid, block, 0, st>>>(p, im, v, f, nn, np, AA, dt, Lv, iLv, q, ctl);
+    if (fin && integ) launch_pdl(k_verlet<true, true>, grid, block, 0, st, p, im, v, f, nn, np, AA, dt, Lv, iLv, q, ctl);
+    else if (integ) launch_pdl(k_verlet<false, true>, grid, block, 0, st, p, im, v, f, nn, np, AA, dt, Lv, iLv, q, ctl);
+    else launch_pdl(k_verlet<true, false>, grid, block, 0, st, p, im, v, f, nn, np, AA, dt, Lv, iLv, q, ctl);
     return check_launch("k_verlet");
 }
 
