@@ -272,13 +272,20 @@ def force_kernel_roofline(s, args, torch, iters=20):
     bytes_alg = n * (32.0 + 4.0 * nbar)
     peak, how = measured_peaks()
     achieved = bytes_alg / t / 1e9
-    # secondary roofline: FP32 lane operations of the packed instruction stream (67 per evaluated list entry:
-    # DESIGN.md "pair force") against 128 lanes x SM count x SM clock
+    # secondary roofline: FP32 lane operations of the packed instruction stream (41 per evaluated list entry in warps
+    # that skip the minimum image, 50 otherwise; the lower count is used: DESIGN.md "pair force") against
+    # 128 lanes x SM count x SM clock
     fp32_peak = 148 * 128 * 1.965e9
+    # DRAM bytes of one launch from the committed ncu --set full capture (same kernel, same workload), scaled to n
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_force_traffic.json")
+    if os.path.exists(tpath) and not isinstance(s, DecomposedAdapter):
+        tj = json.load(open(tpath))
+        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * (n / tj["particles"])
     return {"bound": "hbm", "kernel": "k_force_row2 (packed f32x2, %d lanes per particle)" % args.lanes, "achieved": achieved,
-            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": how, "avg_launch_us": t * 1e6,
+            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": how, "avg_launch_us": t * 1e6,
             "algorithmic_bytes_per_launch": bytes_alg, "mean_list_length": nbar, "pairs_per_s": n * nbar / t,
-            "fp32_lane_ops_frac": n * nbar * 67.0 / t / fp32_peak,
+            "fp32_lane_ops_frac": n * nbar * 41.0 / t / fp32_peak,
             "l2": "flushed between launches (256 MiB write)"}
 
 

@@ -1,14 +1,20 @@
 #!/bin/bash
-# One GPU-box session: GPU tests, launch list of the step loop, full ncu capture of the pair-force kernel, bench.
-# Usage (under gpurun): bash scripts/gpu_round.sh <tag>
+# One GPU-box session: GPU tests, launch list of the steady-state NVE step loop, full ncu captures of the pair-force,
+# neighbour-build and integrator kernels, bench.  Usage (under gpurun): bash scripts/gpu_round.sh <tag>
 tag=${1:-r1}
 out=gpurun_out
 mkdir -p $out
-(timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -15) > $out/${tag}_pytest_gpu.log
-B="python bench.py --steps 1 --warmup 1 --md-steps 100 --melt-steps 1000 --no-cpu-baseline"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 3300 -c 400 --csv \
+(timeout 1000 python -m pytest tests -m gpu -q 2>&1 | tail -6) > $out/${tag}_pytest_gpu.log
+B="python bench.py --steps 1 --warmup 1 --md-steps 300 --melt-steps 600 --no-cpu-baseline"
+# launches: melt 600 steps (~1900 launches incl. rebuilds), then 2 x 300 NVE steps; list the last ~700 launches
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 2600 -c 700 --csv \
     --log-file $out/${tag}_launches.csv $B > $out/${tag}_launches.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_force -s 1200 -c 2 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_force_row2 -s 1500 -c 1 \
     -f -o $out/${tag}_force $B > $out/${tag}_force_ncu.log 2>&1
-(timeout 600 python bench.py 2>&1 | tail -3) > $out/${tag}_bench.log
-tail -5 $out/${tag}_pytest_gpu.log; tail -2 $out/${tag}_launches.log; tail -2 $out/${tag}_force_ncu.log; cat $out/${tag}_bench.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_nlist_build -s 40 -c 1 \
+    -f -o $out/${tag}_nlist $B > $out/${tag}_nlist_ncu.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_verlet -s 700 -c 1 \
+    -f -o $out/${tag}_verlet $B > $out/${tag}_verlet_ncu.log 2>&1
+(timeout 600 python bench.py 2>&1 | tail -1) > $out/${tag}_bench.json
+(timeout 600 python bench.py --impl reference 2>&1 | tail -1) > $out/${tag}_bench_reference.json
+tail -3 $out/${tag}_pytest_gpu.log; tail -1 $out/${tag}_launches.log | cut -c1-200; cut -c1-300 $out/${tag}_bench.json; cut -c1-600 $out/${tag}_bench_reference.json
