@@ -157,6 +157,7 @@ _module_protos = {
     "hxm_force_pair_trunc_create": (C.c_int, [P, P, D3, P, C.c_float, PP]),
     "hxm_force_destroy": (None, [P]),
     "hxm_force_apply": (C.c_int, [P]),
+    "hxm_density_modes": (C.c_int, [P, F3, C.c_uint, P]),
     "hxm_force_add_planar_wall": (C.c_int, [P, C.POINTER(PlanarWall)]),
     "hxm_integrator_verlet_create": (C.c_int, [P, P, D3, C.c_double, PP]),
     "hxm_integrator_andersen_create": (C.c_int, [P, P, D3, C.c_double, C.c_double, C.c_double, C.c_uint, PP]),

@@ -523,6 +523,50 @@ class _wavevector:
         self.value = np.asarray(vecs, dtype=np.float64)
 
 
+class _density_mode:
+    """observables.density_mode{group / particle, wavevector} (lua/halmd/observables/density_mode.lua.in):
+    rho_q = sum_j exp(-i q.r_j) for every wavevector, as a complex array."""
+
+    def __init__(self, group=None, particle=None, wavevector=None):
+        self.particle = particle if particle is not None else getattr(group, "particle", group)
+        if self.particle is None or wavevector is None:
+            raise ValueError("density_mode: missing argument 'group' or 'wavevector'")
+        self.wavevector = wavevector
+
+    def acquire(self):
+        q = np.ascontiguousarray(self.wavevector.value, dtype=np.float32)
+        rho = np.zeros(2 * len(q))
+        check(lib.hxm_density_modes(self.particle._h, hx.farr(q.reshape(-1)), len(q), rho.ctypes.data_as(C.c_void_p)),
+              "density_mode.acquire")
+        return rho[0::2] + 1j * rho[1::2]
+
+
+class _ssf:
+    """observables.ssf{density_mode, norm} (lua/halmd/observables/ssf.lua.in, halmd/observables/ssf.cpp:58-105): per
+    wavenumber shell, mean / error of mean / count of Re[rho1_q conj(rho2_q)] / norm.  `density_mode` is one module
+    or a pair (partial structure factors)."""
+
+    def __init__(self, density_mode=None, norm=None):
+        if density_mode is None or norm is None:
+            raise ValueError("ssf: missing argument 'density_mode' or 'norm'")
+        modes = density_mode if isinstance(density_mode, (list, tuple)) else (density_mode, density_mode)
+        self.mode1, self.mode2 = modes[0], modes[-1]
+        self.wavevector = self.mode1.wavevector
+        self.norm = float(norm)
+
+    def sample(self):
+        rho1 = self.mode1.acquire()
+        rho2 = rho1 if self.mode2 is self.mode1 else self.mode2.acquire()
+        out = np.zeros((len(self.wavevector.shell), 3))
+        for k, (a, b) in enumerate(self.wavevector.shell):
+            re = (rho1[a:b] * np.conj(rho2[a:b])).real / self.norm
+            n = b - a
+            # accumulator.hpp:139-180 — error of mean = sqrt(variance / (count - 1)), variance = m2 / count
+            err = np.sqrt(re.var() / (n - 1)) if n > 1 else 0.0
+            out[k] = (re.mean(), err, n)
+        return out
+
+
 class _blocking_scheme(_Handle):
     """observables.dynamics.blocking_scheme{max_lag, every, size, shift, separation} with the correlation functions
     mean_square_displacement and (given a wavevector module) intermediate_scattering_function."""
@@ -597,5 +641,7 @@ observables = _NS(
     sampler=_sampler(),
     thermodynamics=_thermodynamics,
     utility=_NS(wavevector=_wavevector),
+    density_mode=_density_mode,
+    ssf=_ssf,
     dynamics=_NS(blocking_scheme=_blocking_scheme),
 )

@@ -1115,6 +1115,24 @@ int hxm_core_stats(const hxm_core* c, uint64_t* launches, uint64_t* chunks, uint
 
 int hxm_core_thermodynamics(hxm_core* c, double out[10]) { return (c && out) ? c->thermodynamics(out) : HX_E_INVALID; }
 
+// observables.density_mode:acquire (halmd/observables/gpu/density_mode.cpp:70-131) for the group of all particles
+int hxm_density_modes(hxm_particle* p, const float* wavevector_host, unsigned nq, double* rho_host)
+{
+    if (!p || !wavevector_host || !rho_host || nq == 0) { set_error("density_mode: invalid argument"); return HX_E_INVALID; }
+    float* q = nullptr;
+    double* rho = nullptr;
+    HXM_TRY(dev_alloc(&q, static_cast<size_t>(3) * nq));
+    int rc = dev_alloc(&rho, static_cast<size_t>(2) * nq);
+    if (rc == 0) rc = static_cast<int>(cudaMemcpyAsync(q, wavevector_host, sizeof(float) * 3 * nq, cudaMemcpyHostToDevice, p->st));
+    if (rc == 0) rc = hx_density_modes(reinterpret_cast<const hx_float4*>(p->pos), p->n, q, nq, rho, p->st);
+    if (rc == 0) rc = static_cast<int>(cudaMemcpyAsync(rho_host, rho, sizeof(double) * 2 * nq, cudaMemcpyDeviceToHost, p->st));
+    if (rc == 0) rc = static_cast<int>(cudaStreamSynchronize(p->st));
+    dev_free(q);
+    dev_free(rho);
+    if (rc != 0) set_error("density_mode: failed (code %d)", rc);
+    return rc;
+}
+
 int hxm_blocking_create(hxm_core* core, double max_lag_time, double resolution, unsigned block_size, unsigned shift,
                         unsigned separation, const float* wavevectors, unsigned nq, const unsigned* shell_offsets,
                         unsigned nshell, hxm_blocking** out)

@@ -139,6 +139,9 @@ int hxm_core_stats(const hxm_core* c, uint64_t* launches, uint64_t* chunks, uint
  * [5]=E_tot/N, [6..8]=v_cm, [9]=density  (observables/thermodynamics.hpp:73-86); forces are re-evaluated with
  * auxiliary variables if needed (particle.cpp:221-253) */
 int hxm_core_thermodynamics(hxm_core* c, double out[10]);
+/* observables.density_mode:acquire for all particles (halmd/observables/gpu/density_mode.cpp:70-131):
+ * rho_host[2*k + {0,1}] = (sum cos q_k.r, -sum sin q_k.r); wavevector_host: float[3 * nq] */
+int hxm_density_modes(hxm_particle* p, const float* wavevector_host, unsigned nq, double* rho_host);
 
 /* ---- observables.dynamics.blocking_scheme + correlations ------------------------------------------------------------------ */
 /* blocking_scheme(clock, max_lag, resolution, block_size, shift, separation) with timestep from the integrator;

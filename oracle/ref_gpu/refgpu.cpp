@@ -22,6 +22,7 @@
 #include <halmd/mdsim/gpu/potentials/pair/truncations/shifted_kernel.hpp>
 #include <halmd/mdsim/gpu/potentials/pair/truncations/smooth_r4_kernel.hpp>
 #include <halmd/mdsim/gpu/sorts/hilbert_kernel.hpp>
+#include <halmd/observables/gpu/density_mode_kernel.hpp>
 
 #include <algorithm>
 #include <cstdint>
@@ -406,5 +407,34 @@ extern "C" int refgpu_planar_wall(unsigned nwall, unsigned nspecies, const float
         if ((rc = d_en.down(en_pot))) return rc;
         if ((rc = d_st.down(stress))) return rc;
     }
+    return 0;
+}
+
+// observables::gpu::density_mode::acquire (density_mode.cpp:85-131): block sums of exp(i q.r) per wavevector, then one
+// block per wavevector finalises; the host stores (rho.x, -rho.y).  The group is all particles (identity index).
+extern "C" int refgpu_density_modes(const float* position4, size_t nparticle, const float* q3, unsigned nq, double* rho2)
+{
+    unsigned const blocks = 32, threads = 256;
+    dbuf<float4> d_pos(reinterpret_cast<const float4*>(position4), nparticle);
+    std::vector<float4> h_q(nq);
+    for (unsigned k = 0; k < nq; ++k) h_q[k] = make_float4(q3[3 * k], q3[3 * k + 1], q3[3 * k + 2], 0.f);
+    dbuf<float4> d_q(h_q.data(), nq);
+    std::vector<unsigned int> h_idx(nparticle);
+    for (size_t i = 0; i < nparticle; ++i) h_idx[i] = static_cast<unsigned int>(i);
+    dbuf<unsigned int> d_idx(h_idx.data(), nparticle);
+    dbuf<float2> d_block(static_cast<size_t>(nq) * blocks), d_rho(nq);
+    if (!d_pos.p || !d_q.p || !d_idx.p || !d_block.p || !d_rho.p) return static_cast<int>(cudaErrorMemoryAllocation);
+    lintex<float4> t_q(d_q.p, nq);
+    auto& kernel = observables::gpu::density_mode_wrapper<3>::kernel;
+    RG_TRY(
+        kernel.compute.configure(dim3(blocks), dim3(threads));
+        kernel.compute(t_q.t, d_pos.p, d_idx.p, static_cast<int>(nparticle), d_block.p, static_cast<int>(nq));
+        kernel.finalise.configure(dim3(nq), dim3(threads));
+        kernel.finalise(d_block.p, d_rho.p, static_cast<int>(nq), static_cast<int>(blocks));
+    )
+    RG_CHECK(cudaDeviceSynchronize());
+    std::vector<float2> h(nq);
+    RG_CHECK(static_cast<cudaError_t>(d_rho.down(h.data())));
+    for (unsigned k = 0; k < nq; ++k) { rho2[2 * k] = h[k].x; rho2[2 * k + 1] = -h[k].y; }
     return 0;
 }

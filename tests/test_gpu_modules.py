@@ -434,6 +434,39 @@ def test_slit_pore_external_wall(api):
     assert states[0] == states[1]
 
 
+def test_ssf_of_fcc_lattice(api):
+    """test/unit/observables/ssf.cpp:100-300: density modes and static structure factor of a perfect fcc lattice —
+    rho_q vanishes unless q is a reciprocal lattice vector with (h, k, l) all even or all odd, where |rho_q| = N and
+    S(q) = N; tolerance 50 N epsilon on rho_q as in the reference test."""
+    from halmd_b200 import mdsim, observables
+    from halmd_b200 import simulation
+    ncell = np.array([6, 12, 12])
+    n = 4 * int(np.prod(ncell))
+    a = (4 / 0.3) ** (1 / 3)
+    box = mdsim.box(length=list(ncell * a))
+    p = mdsim.particle(dimension=3, particles=n, species=1)
+    pos = simulation.fcc_positions(n, box.length)
+    p.set("position", pos.astype(np.float32))
+    q_lat = 2 * np.pi / a
+    wavenumber = sorted(set([q_lat / ncell[0], q_lat / ncell[1]] + [np.sqrt(m) * q_lat for m in (1, 2, 3, 4, 5, 6, 8, 9, 10, 12)]))
+    wv = observables.utility.wavevector(box=box, wavenumber=wavenumber, tolerance=1e-3, max_count=6)
+    dm = observables.density_mode(particle=p, wavevector=wv)
+    rho = dm.acquire()
+    assert len(rho) == len(wv.value)
+    hkl = np.rint(wv.value * a / (2 * np.pi) * 1e6) / 1e6
+    integer = np.all(np.abs(hkl - np.rint(hkl)) < 1e-6, axis=1)
+    parity = np.rint(hkl).astype(int) % 2
+    bragg = integer & ((parity.sum(axis=1) == 0) | (parity.sum(axis=1) == 3))
+    tol = 50 * n * 1.1920929e-07
+    assert bragg.any() and (~bragg).any()
+    assert np.all(np.abs(np.abs(rho[bragg]) - n) < tol)
+    assert np.all(np.abs(rho[~bragg]) < tol)
+    s = observables.ssf(density_mode=dm, norm=n).sample()
+    for k, (lo, hi) in enumerate(wv.shell):
+        expect = n * bragg[lo:hi].mean()
+        assert abs(s[k, 0] - expect) < 2 * tol + 1e-3 * expect and s[k, 2] == hi - lo
+
+
 def test_api_errors(api):
     halmd_b200, simulation = api
     from halmd_b200 import mdsim, HxError
