@@ -17,6 +17,7 @@
 #include <halmd/random/gpu/rand48_kernel.cuh>
 #include <halmd/mdsim/gpu/max_displacement_kernel.hpp>
 #include <halmd/mdsim/gpu/neighbours/from_binning_kernel.hpp>
+#include <halmd/mdsim/gpu/particle_kernel.hpp>
 #include <halmd/mdsim/gpu/potentials/pair/lennard_jones_kernel.hpp>
 #include <halmd/mdsim/gpu/potentials/pair/truncations/sharp_kernel.hpp>
 #include <halmd/mdsim/gpu/potentials/pair/truncations/shifted_kernel.hpp>
@@ -437,4 +438,39 @@ extern "C" int refgpu_density_modes(const float* position4, size_t nparticle, co
     RG_CHECK(static_cast<cudaError_t>(d_rho.down(h.data())));
     for (unsigned k = 0; k < nq; ++k) { rho2[2 * k] = h[k].x; rho2[2 * k + 1] = -h[k].y; }
     return 0;
+}
+
+// particle::rearrange (particle.cpp:173-218): gather positions / velocities (double-single: hi and lo planes), images
+// and ids by a permutation through textures; reverse ids are rebuilt by the caller in the reference (particle.cpp:213)
+extern "C" int refgpu_rearrange(const uint32_t* index, size_t nparticle, size_t array_size, const float* position8,
+                                const float* velocity8, const float* image4, const uint32_t* id, float* position8_out,
+                                float* velocity8_out, float* image4_out, uint32_t* id_out)
+{
+    typedef particle_wrapper<3, dsfloat> wrapper_type;
+    typedef wrapper_type::ptr_type ptr_type;
+    if (array_size % 128 != 0) return static_cast<int>(cudaErrorInvalidValue);
+    dbuf<unsigned int> d_index(index, nparticle);
+    dbuf<float4> d_pos(reinterpret_cast<const float4*>(position8), 2 * array_size);
+    dbuf<float4> d_vel(reinterpret_cast<const float4*>(velocity8), 2 * array_size);
+    dbuf<float4> d_img(reinterpret_cast<const float4*>(image4), array_size);
+    dbuf<unsigned int> d_id(id, array_size);
+    dbuf<float4> o_pos(2 * array_size), o_vel(2 * array_size), o_img(array_size);
+    dbuf<unsigned int> o_id(array_size);
+    if (!d_index.p || !d_pos.p || !d_vel.p || !d_img.p || !d_id.p || !o_pos.p || !o_vel.p || !o_img.p || !o_id.p)
+        return static_cast<int>(cudaErrorMemoryAllocation);
+    // texFetch<float4, dsfloat> reads the low word at index + texture size / 2 (dsfloat_cuda_vector layout)
+    lintex<float4> t_r(d_pos.p, 2 * array_size), t_v(d_vel.p, 2 * array_size), t_img(d_img.p, array_size);
+    lintex<unsigned int> t_id(d_id.p, array_size);
+    ptr_type pos = {o_pos.p, o_pos.p + array_size}, vel = {o_vel.p, o_vel.p + array_size};
+    RG_TRY(
+        wrapper_type::kernel.rearrange.configure(dim3(static_cast<unsigned>(array_size / 128)), dim3(128));
+        wrapper_type::kernel.rearrange(t_r.t, t_img.t, t_v.t, t_id.t, d_index.p, pos, o_img.p, vel, o_id.p,
+                                       static_cast<unsigned>(nparticle));
+    )
+    RG_CHECK(cudaDeviceSynchronize());
+    int rc;
+    if ((rc = o_pos.down(reinterpret_cast<float4*>(position8_out)))) return rc;
+    if ((rc = o_vel.down(reinterpret_cast<float4*>(velocity8_out)))) return rc;
+    if ((rc = o_img.down(reinterpret_cast<float4*>(image4_out)))) return rc;
+    return o_id.down(id_out);
 }

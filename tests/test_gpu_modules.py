@@ -434,6 +434,34 @@ def test_slit_pore_external_wall(api):
     assert states[0] == states[1]
 
 
+def test_wetting_slab_config5(api):
+    """BASELINE config 5 at full size: N = 2,000,000 LJ particles between two planar walls (slit pore), Andersen melt,
+    NVE, density modes along the wall normal and the static structure factor parallel to the walls.  Size-independent
+    properties: confinement, energy conservation, layering (the fluid orders against the walls: the density mode at
+    the layer spacing along x dominates the same wavenumber parallel to the walls), particle conservation."""
+    from halmd_b200 import mdsim, observables
+    n, D = 2000000, 60.0
+    box, p, force, integ, e_pair = slit_pore(n=n, D=D, seed=8, timestep=0.002)
+    core = mdsim.core.get()
+    core.run(400)                                                          # Andersen melt at T = 0.9
+    x = p.get("position")[:, 0]
+    assert np.abs(x).max() < (D + 1) / 2
+    mdsim.integrators.verlet(box=box, particle=p, timestep=0.001)
+    core = mdsim.core.get()
+    e0 = core.thermodynamics()["internal_energy"]
+    core.run(300)
+    e1 = core.thermodynamics()["internal_energy"]
+    assert abs(e1 - e0) < 1e-4 * abs(e0), (e0, e1)
+    assert np.array_equal(np.sort(p.get("id")), np.arange(n))
+    Lx, Ly = box.length[0], box.length[1]
+    mx = int(round(Lx / 0.93))                                             # layer spacing ~ 0.93 sigma at the walls
+    class wv:                                                              # two hand-picked wavevectors
+        value = np.array([[2 * np.pi / Lx * mx, 0, 0], [0, 2 * np.pi / Ly * int(round(Ly / 0.93)), 0]])
+        shell = [(0, 1), (1, 2)]
+    s = observables.ssf(density_mode=observables.density_mode(particle=p, wavevector=wv), norm=n).sample()
+    assert s[0, 0] > 3 * s[1, 0], s
+
+
 def test_ssf_of_fcc_lattice(api):
     """test/unit/observables/ssf.cpp:100-300: density modes and static structure factor of a perfect fcc lattice —
     rho_q vanishes unless q is a reciprocal lattice vector with (h, k, l) all even or all odd, where |rho_q| = N and
