@@ -10,6 +10,6 @@ while [ $# -ge 2 ]; do
   /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-O3 -Xptxas -v $flags \
       -c force.cu -o ../../scripts/_build/force_$name.o 2> ../../scripts/_build/force_$name.log
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../scripts/_build/$name.so \
-      core.o binning.o order.o neighbour.o ../../scripts/_build/force_$name.o integrate.o observables.o dd.o modules.o -cudart static
+      core.o binning.o order.o neighbour.o ../../scripts/_build/force_$name.o external.o integrate.o observables.o dd.o modules.o -cudart static
   grep -A2 "k_force_row2ILi2ELi2ELi4" ../../scripts/_build/force_$name.log | grep -E "Used" | sed "s/^/$name: /"
 done
