@@ -23,7 +23,11 @@
 #include <halmd/mdsim/gpu/potentials/pair/truncations/shifted_kernel.hpp>
 #include <halmd/mdsim/gpu/potentials/pair/truncations/smooth_r4_kernel.hpp>
 #include <halmd/mdsim/gpu/sorts/hilbert_kernel.hpp>
+#include <halmd/algorithm/gpu/reduce_kernel.hpp>
+#include <halmd/numeric/accumulator.hpp>
+#include <halmd/observables/dynamics/mean_square_displacement.hpp>
 #include <halmd/observables/gpu/density_mode_kernel.hpp>
+#include <halmd/observables/gpu/dynamics/tagged_particle.hpp>
 
 #include <algorithm>
 #include <cstdint>
@@ -473,4 +477,33 @@ extern "C" int refgpu_rearrange(const uint32_t* index, size_t nparticle, size_t 
     if ((rc = o_vel.down(reinterpret_cast<float4*>(velocity8_out)))) return rc;
     if ((rc = o_img.down(reinterpret_cast<float4*>(image4_out)))) return rc;
     return o_id.down(id_out);
+}
+
+// observables::gpu::dynamics::mean_square_displacement::operator() (mean_square_displacement.cpp:55-68): the
+// reduction kernel instantiated in mean_square_displacement_kernel.cu over zip(first, second) with the
+// tagged_particle<mean_square_displacement<3, float>, dsfloat> accumulator, 32 blocks x 256 threads
+// (defaults, :45-52), block results merged on the host like reduction::operator() (algorithm/gpu/reduce.hpp:101-112).
+// out = (count, mean, variance) of |r2 - r1|^2 over the particles.
+extern "C" int refgpu_msd(const float* first4, const float* second4, size_t nparticle, double out[3])
+{
+    typedef observables::gpu::dynamics::tagged_particle<observables::dynamics::mean_square_displacement<3, float>, dsfloat> acc_type;
+    unsigned const blocks = 32, threads = 256;
+    dbuf<float4> d_a(reinterpret_cast<const float4*>(first4), nparticle), d_b(reinterpret_cast<const float4*>(second4), nparticle);
+    dbuf<acc_type> d_block(blocks);
+    if (!d_a.p || !d_b.p || !d_block.p) return static_cast<int>(cudaErrorMemoryAllocation);
+    auto& kernel = reduction_kernel<acc_type>::kernel;
+    RG_TRY(
+        kernel.reduce.configure(dim3(blocks), dim3(threads));
+        acc_type::iterator first(std::make_tuple(static_cast<float4 const*>(d_a.p), static_cast<float4 const*>(d_b.p)));
+        kernel.reduce(first, static_cast<std::ptrdiff_t>(nparticle), d_block.p, acc_type());
+    )
+    RG_CHECK(cudaDeviceSynchronize());
+    std::vector<acc_type> h(blocks);
+    RG_CHECK(static_cast<cudaError_t>(d_block.down(h.data())));
+    acc_type total;
+    for (unsigned i = 0; i < blocks; ++i) total(h[i]);
+    out[0] = static_cast<double>(count(total()));
+    out[1] = static_cast<double>(mean(total()));
+    out[2] = static_cast<double>(variance(total()));
+    return 0;
 }
