@@ -100,6 +100,8 @@ _protos = {
     "hx_rand48_seed": (C.c_int, [C.POINTER(Rand48), C.c_uint, C.c_uint, C.c_uint, P, P]),
     "hx_rand48_uniform": (C.c_int, [C.POINTER(Rand48), P, P, SZ, P]),
     "hx_andersen_finalize": (C.c_int, [P, P, SZ, SZ, C.c_float, C.c_float, C.c_float, C.POINTER(Rand48), P, P]),
+    "hx_andersen_scratch_bytes": (SZ, [SZ]),
+    "hx_andersen_finalize2": (C.c_int, [P, P, SZ, SZ, C.c_float, C.c_float, C.c_float, C.POINTER(Rand48), P, P, SZ, P, P]),
     "hx_andersen_finalize_guarded": (C.c_int, [P, P, SZ, SZ, C.c_float, C.c_float, C.c_float,
                                                C.POINTER(Rand48), P, P, P]),
     "hx_sample_positions": (C.c_int, [P, P, P, SZ, F3, P, P]),

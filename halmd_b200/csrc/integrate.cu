@@ -266,6 +266,94 @@ __global__ void k_andersen_finalize(float4* __restrict__ vel, const float4* __re
     r48_unpack(g.s, state + 3 * t);
 }
 
+// ---- Andersen thermostat in two passes --------------------------------------------------------------------------------
+// The reference kernel above is sequential by construction: 8192 generator threads walk the particle array with a
+// grid stride, and what a thread draws at one particle depends on the collisions of its warp at all earlier ones
+// (warp-wide vote, cached second variate, rejection loops of the polar method).  At 10^6 particles that is 122
+// dependent iterations of memory traffic, double-single arithmetic, log and sqrt on a quarter of a percent of the
+// machine (100 us where the memory traffic needs 12).  The same stream is reproduced in two passes:
+//   plan     (generator grid, sequential per thread): only the generator bookkeeping — the uniform variate of the
+//            collision test, the warp vote, the rejection loops — recording, per particle-warp, whether it collides
+//            and, per colliding particle, the generator states at which its accepted variate pairs start;
+//   apply    (one thread per particle): half-kick, or Box-Muller from the recorded states.
+// Same functions on the same states: velocities and generator state are bit-identical to the one-pass kernel
+// (tests/test_gpu_kernels.py::test_andersen_two_pass_equals_one_pass).
+__device__ __forceinline__ unsigned long long accepted_pair_state(r48& g)
+{
+    unsigned long long s0;
+    float s;
+    do {
+        s0 = g.s;
+        float v1 = __fmaf_rn(2.f, g.uniform(), -1.f);
+        float v2 = __fmaf_rn(2.f, g.uniform(), -1.f);
+        s = __fmaf_rn(v1, v1, __fmul_rn(v2, v2));
+    } while (s >= 1.f);
+    return s0;
+}
+
+__global__ void k_andersen_plan(unsigned n, float q, uint16_t* __restrict__ state, unsigned long long ra, unsigned long long rc,
+                                unsigned char* __restrict__ collide, unsigned long long* __restrict__ plan_xy,
+                                unsigned long long* __restrict__ plan_z, const unsigned* __restrict__ ctl)
+{
+    if (ctl && ctl[CTL_HALTED]) return;
+    unsigned const t = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned const T = gridDim.x * blockDim.x;
+    r48 g = {r48_pack(state + 3 * t), ra, rc};
+    bool cached = false;
+    unsigned long long last_z = 0;
+    unsigned const warp_base = t & ~31u;
+    for (unsigned base = warp_base; base < n; base += T) {
+        unsigned i = base + (t & 31u);
+        bool const valid = i < n;
+        unsigned const active = __ballot_sync(0xFFFFFFFFu, valid);
+        if (!valid) continue;
+        bool const no_coll = g.uniform() > q;
+        bool const det = __all_sync(active, no_coll);
+        if ((t & 31u) == 0) collide[base >> 5] = det ? 0 : 1;
+        if (!det) {
+            plan_xy[i] = accepted_pair_state(g);
+            if ((cached = !cached)) {
+                last_z = accepted_pair_state(g);
+                plan_z[i] = last_z;                         // first variate of a new pair
+            } else {
+                plan_z[i] = last_z | (1ull << 63);          // cached second variate of the previous pair
+            }
+        }
+    }
+    r48_unpack(g.s, state + 3 * t);
+}
+
+__global__ void __launch_bounds__(128) k_andersen_apply(float4* __restrict__ vel, const float4* __restrict__ force, unsigned n,
+                                                       unsigned A, float dt, float sqrt_temperature, unsigned long long ra,
+                                                       unsigned long long rc, const unsigned char* __restrict__ collide,
+                                                       const unsigned long long* __restrict__ plan_xy,
+                                                       const unsigned long long* __restrict__ plan_z,
+                                                       const unsigned* __restrict__ ctl)
+{
+    if (ctl && ctl[CTL_HALTED]) return;
+    unsigned const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 const vh = vel[i];
+    float const mass = vh.w;
+    if (!collide[i >> 5]) {
+        float4 const vl = vel[i + A];
+        float4 const f = force[i];
+        ds3 v = {make_ds(vh.x, vl.x), make_ds(vh.y, vl.y), make_ds(vh.z, vl.z)};
+        half_kick(v, f, __fmul_rn(dt, 0.5f), mass);
+        vel[i] = make_float4(v.x.hi, v.y.hi, v.z.hi, mass);
+        vel[i + A] = make_float4(v.x.lo, v.y.lo, v.z.lo, 0.f);
+    } else {
+        float vx, vy, z1, z2;
+        r48 gx = {plan_xy[i], ra, rc};
+        normal_pair(gx, sqrt_temperature, vx, vy);
+        unsigned long long const pz = plan_z[i];
+        r48 gz = {pz & R48_MASK, ra, rc};
+        normal_pair(gz, sqrt_temperature, z1, z2);
+        vel[i] = make_float4(vx, vy, (pz >> 63) ? z2 : z1, mass);
+        vel[i + A] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 } // namespace hx
 
 using namespace hx;
@@ -456,6 +544,40 @@ static int andersen_launch(hx_float4* velocity_dev, const hx_float4* force_dev, 
         static_cast<unsigned>(nparticle), static_cast<unsigned>(array_size), timestep, sqrt_temperature, q, state_dev,
         r48_pack(rng->a), r48_pack(rng->c), ctl);
     return check_launch("k_andersen_finalize");
+}
+
+size_t hx_andersen_scratch_bytes(size_t nparticle)
+{
+    // collision flag per particle-warp (padded to 8 bytes) + two generator states per particle
+    return ((nparticle + 31) / 32 + 7) / 8 * 8 + 2 * sizeof(unsigned long long) * nparticle;
+}
+
+int hx_andersen_finalize2(hx_float4* velocity_dev, const hx_float4* force_dev, size_t nparticle, size_t array_size,
+                          float timestep, float sqrt_temperature, float coll_prob, const hx_rand48* rng,
+                          uint16_t* state_dev, void* scratch_dev, size_t scratch_bytes, const uint32_t* ctl_dev, void* stream)
+{
+    if (!velocity_dev || !force_dev || !rng || !state_dev || !scratch_dev || nparticle > array_size
+        || array_size >= 0x7FFFFFFFull || scratch_bytes < hx_andersen_scratch_bytes(nparticle)) {
+        set_error("hx_andersen_finalize2: invalid argument");
+        return HX_E_INVALID;
+    }
+    if (nparticle == 0) return HX_OK;
+    float const q = 1.f - powf(1.f - coll_prob, 1.f / 32);      // as andersen_launch
+    size_t const flag_bytes = ((nparticle + 31) / 32 + 7) / 8 * 8;
+    unsigned char* collide = static_cast<unsigned char*>(scratch_dev);
+    unsigned long long* plan_xy = reinterpret_cast<unsigned long long*>(collide + flag_bytes);
+    unsigned long long* plan_z = plan_xy + nparticle;
+    unsigned const n = static_cast<unsigned>(nparticle);
+    cudaStream_t st = as_stream(stream);
+    k_andersen_plan<<<rng->blocks, rng->threads, 0, st>>>(n, q, state_dev, r48_pack(rng->a), r48_pack(rng->c), collide, plan_xy,
+                                                         plan_z, ctl_dev);
+    int rc = check_launch("k_andersen_plan");
+    if (rc != HX_OK) return rc;
+    k_andersen_apply<<<div_up(nparticle, 128), 128, 0, st>>>(
+        reinterpret_cast<float4*>(velocity_dev), reinterpret_cast<const float4*>(force_dev), n,
+        static_cast<unsigned>(array_size), timestep, sqrt_temperature, r48_pack(rng->a), r48_pack(rng->c), collide, plan_xy,
+        plan_z, ctl_dev);
+    return check_launch("k_andersen_apply");
 }
 
 int hx_andersen_finalize(hx_float4* velocity_dev, const hx_float4* force_dev, size_t nparticle, size_t array_size,

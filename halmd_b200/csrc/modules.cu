@@ -348,8 +348,9 @@ struct hxm_integrator {
     float sqrt_temperature = 1, coll_prob = 0;
     hx_rand48 rng;
     uint16_t* rng_state = nullptr;
+    unsigned char* andersen_scratch = nullptr;
 
-    ~hxm_integrator() { dev_free(rng_state); }
+    ~hxm_integrator() { dev_free(rng_state); dev_free(andersen_scratch); }
 
     void update_andersen()
     {
@@ -379,11 +380,9 @@ struct hxm_integrator {
             return hx_verlet_finalize(reinterpret_cast<hx_float4*>(p->vel), reinterpret_cast<hx_float4*>(p->force), p->A,
                                       static_cast<float>(timestep), p->st);
         }
-        if (ctl) return hx_andersen_finalize_guarded(reinterpret_cast<hx_float4*>(p->vel), reinterpret_cast<hx_float4*>(p->force),
-                                                     p->n, p->A, static_cast<float>(timestep), sqrt_temperature, coll_prob,
-                                                     &rng, rng_state, ctl, p->st);
-        return hx_andersen_finalize(reinterpret_cast<hx_float4*>(p->vel), reinterpret_cast<hx_float4*>(p->force), p->n, p->A,
-                                    static_cast<float>(timestep), sqrt_temperature, coll_prob, &rng, rng_state, p->st);
+        return hx_andersen_finalize2(reinterpret_cast<hx_float4*>(p->vel), reinterpret_cast<hx_float4*>(p->force), p->n, p->A,
+                                     static_cast<float>(timestep), sqrt_temperature, coll_prob, &rng, rng_state,
+                                     andersen_scratch, hx_andersen_scratch_bytes(p->n), ctl, p->st);
     }
 
     int finalize()
@@ -1055,6 +1054,7 @@ int hxm_integrator_andersen_create(hxm_particle* particle, hxm_force* force, con
     i->update_andersen();
     // random/gpu/random.cpp:94-101 — 32 blocks x 256 threads
     HXM_TRY(dev_alloc(&i->rng_state, 3 * 32 * 256));
+    HXM_TRY(dev_alloc(&i->andersen_scratch, hx_andersen_scratch_bytes(particle->n)));
     HXM_TRY(hx_rand48_seed(&i->rng, 32, 256, seed, i->rng_state, particle->st));
     *out = guard.release();
     return 0;

@@ -241,6 +241,15 @@ int hx_andersen_finalize(hx_float4* velocity_dev, const hx_float4* force_dev, si
                          float coll_prob, const hx_rand48* rng, uint16_t* state_dev,
                          void* stream);
 
+/* The same thermostat step in two passes (generator bookkeeping on the RNG grid, then one thread per particle): the
+ * same generator stream and bit-identical velocities at a fraction of the time for large systems.  scratch_dev:
+ * hx_andersen_scratch_bytes(nparticle) bytes; ctl_dev may be NULL (see hx_andersen_finalize_guarded). */
+size_t hx_andersen_scratch_bytes(size_t nparticle);
+int hx_andersen_finalize2(hx_float4* velocity_dev, const hx_float4* force_dev, size_t nparticle,
+                          size_t array_size, float timestep, float sqrt_temperature, float coll_prob,
+                          const hx_rand48* rng, uint16_t* state_dev, void* scratch_dev, size_t scratch_bytes,
+                          const uint32_t* ctl_dev, void* stream);
+
 /* ---- a14-a16: observables -------------------------------------------------------------------
  * halmd/observables/gpu/phase_space_kernel.cu:39-66 (unfolded positions in id order),
  * halmd/observables/gpu/dynamics/mean_square_displacement.cpp:55-68 + tagged_particle.hpp,

@@ -574,6 +574,33 @@ def test_andersen_finalize(hx, oracle, dev, n):
     assert np.allclose(gv[:n, :3], ov[:n, :3], rtol=4e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize("n", [1000, 8192 * 3 + 77, 300000])
+def test_andersen_two_pass_equals_one_pass(hx, dev, n):
+    """hx_andersen_finalize2 (plan on the generator grid + one thread per particle) reproduces the reference-shaped
+    one-pass kernel bit for bit over several rounds: velocities (high and low words) and generator state."""
+    L, p, v, A = lj_fluid(n, 0.8442, 57)
+    rng_np = np.random.default_rng(57)
+    v[:n, 3] = rng_np.choice(np.array([1.0, 1.7, 0.6], dtype=np.float32), n)
+    f = np.zeros((A, 4), dtype=np.float32)
+    f[:n, :3] = rng_np.normal(scale=5, size=(n, 3))
+    rng = hx.Rand48()
+    d_state = dev.zeros(3 * 32 * 256, np.uint16)
+    hx.check(hx.lib.hx_rand48_seed(C.byref(rng), 32, 256, 13, dev.p(d_state), dev.stream))
+    d_state2 = dev.up(dev.down(d_state))
+    d_v, d_v2, d_f = dev.up(v), dev.up(v), dev.up(f)
+    sb = hx.lib.hx_andersen_scratch_bytes(n)
+    d_scr = dev.up(np.full(sb, 0xAB, dtype=np.uint8))                 # poison: nothing stale may be read
+    dt, sqT, prob = 0.005, float(np.sqrt(np.float32(0.7))), 0.1
+    for rnd in range(4):
+        hx.check(hx.lib.hx_andersen_finalize(dev.p(d_v), dev.p(d_f), n, A, dt, sqT, prob, C.byref(rng), dev.p(d_state), dev.stream))
+        hx.check(hx.lib.hx_andersen_finalize2(dev.p(d_v2), dev.p(d_f), n, A, dt, sqT, prob, C.byref(rng), dev.p(d_state2),
+                                              dev.p(d_scr), sb, None, dev.stream))
+        assert np.array_equal(dev.down(d_state), dev.down(d_state2))
+        a, b = dev.down(d_v), dev.down(d_v2)
+        assert a[:n].tobytes() == b[:n].tobytes() and a[A:A + n].tobytes() == b[A:A + n].tobytes()
+    assert np.any(np.all(a[A:A + n, :3] == 0, axis=1))                # collisions happened
+
+
 # ---- a14-a16 observables -----------------------------------------------------------------------------------------
 
 def test_sample_positions_and_msd(hx, oracle, dev):
