@@ -27,8 +27,21 @@ def sorted_lists(s):
     return torch.from_numpy(rows.view(np.int32).copy()).cuda()
 
 
+def kernel_lib():
+    """HALMD_B200_KERNEL_LIB: a second build of the library used for the timed kernel call only (the system is set up
+    and melted with the regular library), so that diagnostic kernel variants see the same physical state."""
+    path = os.environ.get("HALMD_B200_KERNEL_LIB")
+    if not path:
+        return hx.lib
+    lib = C.CDLL(path)
+    for name in ("hx_pair_force", "hx_pair_force_set_lanes"):
+        getattr(lib, name).restype = getattr(hx.lib, name).restype
+        getattr(lib, name).argtypes = getattr(hx.lib, name).argtypes
+    return lib
+
+
 def time_force(s, lanes, flush, iters=20, lists=None, flags=0):
-    lib = hx.lib
+    lib = kernel_lib()
     p, nb, pot = s.particle, s.neighbour, s.potential
     hx.check(lib.hx_pair_force_set_lanes(lanes))
     n = p.nparticle
@@ -44,7 +57,7 @@ def time_force(s, lanes, flush, iters=20, lists=None, flags=0):
             fl.fill_(float(i))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        hx.check(lib.hx_pair_force(C.byref(par), pos, pos, (lists.data_ptr() if lists is not None else lib.hxm_neighbour_device_ptr(nb._h)), nb.size, nb.stride, nb.layout | flags, n,
+        hx.check(lib.hx_pair_force(C.byref(par), pos, pos, (lists.data_ptr() if lists is not None else hx.lib.hxm_neighbour_device_ptr(nb._h)), nb.size, nb.stride, nb.layout | flags, n,
                                    L, 1, 0.5, force.data_ptr(), None, None, p.array_size, C.c_void_p(stream.cuda_stream)))
         e1.record(stream)
         torch.cuda.synchronize()
@@ -69,7 +82,7 @@ def main():
         for lanes in (2, 4, 8):
             for flags in (0, hx.FORCE_POSITIONS_REDUCED):
                 avg, best = time_force(s, lanes, True, flags=flags)
-                print(json.dumps(dict(lib=os.path.basename(hx.LIB_PATH), lanes=lanes, reduced=int(flags != 0), avg_us=round(avg, 2),
+                print(json.dumps(dict(lib=os.path.basename(os.environ.get('HALMD_B200_KERNEL_LIB') or hx.LIB_PATH), lanes=lanes, reduced=int(flags != 0), avg_us=round(avg, 2),
                                       min_us=round(best, 2))), flush=True)
         if a.sorted:
             srt = sorted_lists(s)
