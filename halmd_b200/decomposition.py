@@ -502,13 +502,15 @@ class DecomposedSystem:
             self._p(self.ctl) if (guarded or integrate) else None, self.st), "verlet")
 
     def _andersen(self, guarded):
+        # two-pass thermostat (same generator stream as the reference-shaped kernel, one thread per particle)
         hx = self.hx
-        fn = self.lib.hx_andersen_finalize_guarded if guarded else self.lib.hx_andersen_finalize
-        args = [self._p(self.vel), self._p(self.force), self.n_own, self.cap, self.dt, self.sqrt_temperature, self.coll_prob,
-                C.byref(self.rng), self._p(self.rng_state)]
-        if guarded:
-            args.append(self._p(self.ctl))
-        hx.check(fn(*args, self.st), "andersen")
+        need = int(self.lib.hx_andersen_scratch_bytes(self.own_cap))
+        if getattr(self, "andersen_scratch", None) is None or self.andersen_scratch.numel() < need:
+            self.andersen_scratch = self.torch.empty(need, dtype=self.torch.uint8, device=self.vel.device)
+        hx.check(self.lib.hx_andersen_finalize2(self._p(self.vel), self._p(self.force), self.n_own, self.cap, self.dt,
+                                                self.sqrt_temperature, self.coll_prob, C.byref(self.rng), self._p(self.rng_state),
+                                                self._p(self.andersen_scratch), need, self._p(self.ctl) if guarded else None,
+                                                self.st), "andersen")
 
     def _ensure_force(self):
         if not self.lists_valid:
