@@ -28,7 +28,7 @@ class LjParams(C.Structure):
         ("ntype1", C.c_uint), ("ntype2", C.c_uint), ("truncation", C.c_int), ("rri_smooth", C.c_float),
         ("epsilon", C.c_float * MAX_PAIR_TYPES), ("sigma2", C.c_float * MAX_PAIR_TYPES),
         ("r_cut", C.c_float * MAX_PAIR_TYPES), ("rr_cut", C.c_float * MAX_PAIR_TYPES),
-        ("en_cut", C.c_float * MAX_PAIR_TYPES),
+        ("en_cut", C.c_float * MAX_PAIR_TYPES), ("force_cut", C.c_float * MAX_PAIR_TYPES),
     ]
 
 

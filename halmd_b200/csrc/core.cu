@@ -133,7 +133,7 @@ int hx_potential_lj_init(hx_lj_params* p, unsigned ntype1, unsigned ntype2, cons
         set_error("hx_potential_lj_init: invalid argument (ntype1*ntype2 must be in 1..%d)", HX_MAX_PAIR_TYPES);
         return HX_E_INVALID;
     }
-    if (truncation < HX_TRUNC_SHARP || truncation > HX_TRUNC_SMOOTH_R4) {
+    if (truncation < HX_TRUNC_SHARP || truncation > HX_TRUNC_FORCE_SHIFTED) {
         set_error("hx_potential_lj_init: unknown truncation %d", truncation);
         return HX_E_UNSUPPORTED;
     }
@@ -154,11 +154,14 @@ int hx_potential_lj_init(hx_lj_params* p, unsigned ntype1, unsigned ntype2, cons
         float r6i = rri * rri * rri;
         float eps_r6i = eps * r6i;
         float en_cut = 4 * eps_r6i * (r6i - 1);
+        float fval_cut = 48 * rri * eps_r6i * (r6i - 0.5f) / sigma2;
         p->epsilon[i] = eps;
         p->sigma2[i] = sigma2;
         p->r_cut[i] = r_cut;
         p->rr_cut[i] = rr_cut;
         p->en_cut[i] = (truncation == HX_TRUNC_SHARP) ? 0.f : en_cut;
+        // force_shifted.hpp:69-70 — force_cut = fval(rr_cut) * r_cut
+        p->force_cut[i] = (truncation == HX_TRUNC_FORCE_SHIFTED) ? fval_cut * r_cut : 0.f;
     }
     return HX_OK;
 }

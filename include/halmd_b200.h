@@ -54,6 +54,7 @@ extern "C" {
 #define HX_TRUNC_SHARP     0
 #define HX_TRUNC_SHIFTED   1
 #define HX_TRUNC_SMOOTH_R4 2
+#define HX_TRUNC_FORCE_SHIFTED 3   /* truncations/force_shifted_kernel.cuh:52-63 */
 
 #define HX_MAX_PAIR_TYPES 16 /* ntype1*ntype2 <= 16 */
 
@@ -156,6 +157,7 @@ typedef struct hx_lj_params {
     float r_cut[HX_MAX_PAIR_TYPES];   /* cutoff * sigma */
     float rr_cut[HX_MAX_PAIR_TYPES];
     float en_cut[HX_MAX_PAIR_TYPES];  /* U(r_cut), 0 for sharp */
+    float force_cut[HX_MAX_PAIR_TYPES]; /* |F(r_cut)| = fval(r_cut) * r_cut (force_shifted.hpp:69-70), else 0 */
 } hx_lj_params;
 
 int hx_potential_lj_init(hx_lj_params* p, unsigned ntype1, unsigned ntype2, const float* epsilon,

@@ -347,9 +347,9 @@ int oracle_nlist_build(const uint32_t* g_cell, const unsigned nc[3], unsigned ce
 /* ---- Lennard-Jones + truncations (float = GPU functors, double = host functors) --------------------------- */
 typedef struct {
     unsigned ntype1, ntype2;
-    int truncation;            /* 0 sharp, 1 shifted, 2 smooth_r4 */
+    int truncation;            /* 0 sharp, 1 shifted, 2 smooth_r4, 3 force_shifted */
     float rri_smooth;
-    float epsilon[MAXPT], sigma2[MAXPT], r_cut[MAXPT], rr_cut[MAXPT], en_cut[MAXPT];
+    float epsilon[MAXPT], sigma2[MAXPT], r_cut[MAXPT], rr_cut[MAXPT], en_cut[MAXPT], force_cut[MAXPT];
 } lj_params;
 
 /* lennard_jones_kernel.hpp:43-56 */
@@ -379,6 +379,7 @@ void oracle_lj_init(lj_params* p, unsigned nt1, unsigned nt2, const float* eps, 
         float f, e;
         lj_f(p->rr_cut[i], p->sigma2[i], p->epsilon[i], &f, &e);
         p->en_cut[i] = trunc == 0 ? 0.f : e;
+        p->force_cut[i] = trunc == 3 ? f * p->r_cut[i] : 0.f;      /* force_shifted.hpp:69-70 */
     }
 }
 
@@ -401,6 +402,11 @@ int oracle_pair_f(const lj_params* p, unsigned idx, float rr, float* fval, float
         float h1 = 4 * dr * p->rri_smooth * x2 * x4i * x4i;
         *fval = h0 * *fval - h1 * (e / r);
         *en = h0 * e;
+    } else if (p->truncation == 3) {
+        /* force_shifted_kernel.cuh:52-63 */
+        float r = sqrtf(rr);
+        *fval = *fval - p->force_cut[idx] / r;
+        *en = *en - p->en_cut[idx] + (r - p->r_cut[idx]) * p->force_cut[idx];
     }
     return 1;
 }
@@ -432,6 +438,13 @@ void oracle_pair_d(double eps, double sigma, double cutoff_sigma, int trunc, dou
         double h1 = 4 * dr * rri_smooth * x2 * x4i * x4i;
         f = h0 * f - h1 * (e / r);
         e = h0 * e;
+    } else if (trunc == 3) {
+        /* host/potentials/pair/truncations/force_shifted.hpp: F_c = fval(r_c) r_c */
+        double rric = sigma2 / rr_cut, r6ic = rric * rric * rric;
+        double force_cut = 48 * rric * (eps * r6ic) * (r6ic - 0.5) / sigma2 * r_cut;
+        double r = sqrt(rr);
+        f -= force_cut / r;
+        e = e - en_cut + (r - r_cut) * force_cut;
     }
     *fval = f;
     *en = e;

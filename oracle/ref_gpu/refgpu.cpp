@@ -19,6 +19,7 @@
 #include <halmd/mdsim/gpu/neighbours/from_binning_kernel.hpp>
 #include <halmd/mdsim/gpu/particle_kernel.hpp>
 #include <halmd/mdsim/gpu/potentials/pair/lennard_jones_kernel.hpp>
+#include <halmd/mdsim/gpu/potentials/pair/truncations/force_shifted_kernel.hpp>
 #include <halmd/mdsim/gpu/potentials/pair/truncations/sharp_kernel.hpp>
 #include <halmd/mdsim/gpu/potentials/pair/truncations/shifted_kernel.hpp>
 #include <halmd/mdsim/gpu/potentials/pair/truncations/smooth_r4_kernel.hpp>
@@ -316,12 +317,14 @@ int launch_force(potential_type const& pot, const float4* pos, cudaTextureObject
 
 } // namespace
 
-// truncation: 0 sharp, 1 shifted, 2 smooth_r4.  Parameter tables [ntype * ntype] as lennard_jones.cpp:60-105 and
+// truncation: 0 sharp, 1 shifted, 2 smooth_r4, 3 force_shifted (force_cut table passed through `en_pot`-independent
+// argument force_cut, may be NULL otherwise).  Parameter tables [ntype * ntype] as lennard_jones.cpp:60-105 and
 // truncations/{sharp,shifted,smooth_r4}.hpp upload them: (epsilon, sigma2); rr_cut; (rr_cut, en_cut);
 // (r_cut, rr_cut, en_cut); rri_smooth = h^-2 (smooth_r4.hpp:97).
 // force (in/out, array_size float4); en_pot (array_size) and stress (6 * array_size) may both be NULL (no aux).
 extern "C" int refgpu_pair_force(int truncation, unsigned ntype, const float* epsilon, const float* sigma2, const float* r_cut,
-                                 const float* rr_cut, const float* en_cut, float rri_smooth, const float* position4,
+                                 const float* rr_cut, const float* en_cut, const float* force_cut, float rri_smooth,
+                                 const float* position4,
                                  size_t array_size, const uint32_t* g_neighbour, unsigned size, size_t stride, int layout,
                                  const float box_length[3], int force_zero, float aux_weight, float* force4, float* en_pot,
                                  float* stress)
@@ -329,16 +332,18 @@ extern "C" int refgpu_pair_force(int truncation, unsigned ntype, const float* ep
     if (array_size % 256 != 0) return static_cast<int>(cudaErrorInvalidValue);
     unsigned const np = ntype * ntype;
     std::vector<float2> h_lj(np), h_sh(np);
-    std::vector<float4> h_sm(np);
+    std::vector<float4> h_sm(np), h_fs(np);
     std::vector<float> h_sp(np);
     for (unsigned t = 0; t < np; ++t) {
         h_lj[t] = make_float2(epsilon[t], sigma2[t]);                 // lennard_jones_kernel::EPSILON, SIGMA2
         h_sm[t] = make_float4(r_cut[t], rr_cut[t], en_cut[t], 0.f);   // smooth_r4_kernel::R_CUT, RR_CUT, EN_CUT
         h_sh[t] = make_float2(rr_cut[t], en_cut[t]);                  // shifted_kernel::RR_CUT, EN_CUT
         h_sp[t] = rr_cut[t];
+        // force_shifted_kernel::R_CUT, RR_CUT, EN_CUT, FORCE_CUT
+        h_fs[t] = make_float4(r_cut[t], rr_cut[t], en_cut[t], force_cut ? force_cut[t] : 0.f);
     }
     dbuf<float2> d_lj(h_lj.data(), np), d_sh(h_sh.data(), np);
-    dbuf<float4> d_sm(h_sm.data(), np);
+    dbuf<float4> d_sm(h_sm.data(), np), d_fs(h_fs.data(), np);
     dbuf<float> d_sp(h_sp.data(), np);
     size_t const nl_len = static_cast<size_t>(size) * stride;
     dbuf<float4> d_pos(reinterpret_cast<const float4*>(position4), array_size);
@@ -348,7 +353,7 @@ extern "C" int refgpu_pair_force(int truncation, unsigned ntype, const float* ep
     dbuf<float> d_en(en_pot, aux ? array_size : 0), d_st(stress, aux ? 6 * array_size : 0);
     if (!d_pos.p || !d_nl.p || !d_f.p || !d_en.p || !d_st.p) return static_cast<int>(cudaErrorMemoryAllocation);
     lintex<float2> t_lj(d_lj.p, np), t_sh(d_sh.p, np);
-    lintex<float4> t_sm(d_sm.p, np), t_r2(d_pos.p, array_size);
+    lintex<float4> t_sm(d_sm.p, np), t_fs(d_fs.p, np), t_r2(d_pos.p, array_size);
     lintex<float> t_sp(d_sp.p, np);
     lj::lennard_jones const parent(t_lj.t);
     float* const en = aux ? d_en.p : nullptr;
@@ -358,6 +363,9 @@ extern "C" int refgpu_pair_force(int truncation, unsigned ntype, const float* ep
     if (truncation == 2) {
         RG_TRY(tr::smooth_r4_wrapper<lj::lennard_jones>::rri_smooth.set(rri_smooth))
         tr::smooth_r4_kernel::smooth_r4<lj::lennard_jones> pot(parent, t_sm.t);
+        rc = launch_force(pot, d_pos.p, t_r2.t, d_f.p, d_nl.p, size, pitch, layout, en, st, ntype, box_length, force_zero != 0, aux_weight, array_size);
+    } else if (truncation == 3) {
+        tr::force_shifted_kernel::force_shifted<lj::lennard_jones> pot(parent, t_fs.t);
         rc = launch_force(pot, d_pos.p, t_r2.t, d_f.p, d_nl.p, size, pitch, layout, en, st, ntype, box_length, force_zero != 0, aux_weight, array_size);
     } else if (truncation == 1) {
         tr::shifted_kernel::shifted<lj::lennard_jones> pot(parent, t_sh.t);

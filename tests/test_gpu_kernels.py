@@ -336,7 +336,7 @@ def check_force(f, of, n, tol=ORACLE_TOL):
 
 
 @pytest.mark.parametrize("layout", [0, 1])
-@pytest.mark.parametrize("trunc", [0, 1, 2])
+@pytest.mark.parametrize("trunc", [0, 1, 2, 3])
 def test_pair_force_lj_single_species(hx, oracle, dev, layout, trunc):
     s = build_lists(hx, oracle, dev, 4000, 0.8442, 31, [2.5], 0.5, 0.5, 0.4, layout=layout, fill_all=0)
     f, e, st, of, oe, os_ = run_force(hx, oracle, dev, s, trunc, aux=True, eps=[1.0], sigma=[1.0], cut=[2.5])
@@ -364,7 +364,7 @@ def test_pair_force_binary_mixture(hx, oracle, dev, layout, lanes):
 
 
 @pytest.mark.parametrize("lanes", [2, 4, 8])
-@pytest.mark.parametrize("trunc", [0, 1, 2])
+@pytest.mark.parametrize("trunc", [0, 1, 2, 3])
 @pytest.mark.parametrize("eps,sigma", [(1.0, 1.0), (1.3, 0.9)])
 def test_pair_force_packed_row_kernel(hx, oracle, dev, lanes, trunc, eps, sigma):
     """The production kernel (row layout, no aux, one species: packed f32x2 stream) in every truncation, lane count
@@ -407,7 +407,7 @@ def test_pair_potential_golden_chain(hx, oracle, dev):
     eps, sigma = [1.0, 0.5, 0.5, 0.25], [1.0, 2.0, 2.0, 4.0]
     idx = {"aa": (0, 0), "ab": (0, 1), "bb": (1, 1)}
     L = np.array([100.0, 100.0, 100.0])
-    for trunc_name, trunc in (("sharp", 0), ("shifted", 1), ("smooth_r4", 2)):
+    for trunc_name, trunc in (("sharp", 0), ("shifted", 1), ("smooth_r4", 2), ("force_shifted", 3)):
         rows = []
         for pair, (ta, tb) in idx.items():
             for r, fval, en in g["lennard_jones"][trunc_name][pair]:
@@ -440,6 +440,8 @@ def test_pair_potential_golden_chain(hx, oracle, dev):
             tol = 10 * EPS_F + 14 * abs(r_eff - r) / r + 2e-6
             if trunc == 2:
                 tol += 8 * EPS_F * (1 + rc / (rc - r))
+            if trunc == 3:
+                tol += 5e2 * 10 * EPS_F        # lennard_jones.cpp:266-271
             assert abs(f[2 * k, 0] - fval * dx) <= tol * abs(fval * dx) + 1e-30, (trunc_name, k, f[2 * k, 0], fval * dx)
             ref_en = abs(en) if abs(en) > 1e-3 * 4 * eps[2 * ta + tb] * (sigma[2 * ta + tb] / r) ** 12 else 4 * eps[2 * ta + tb] * (sigma[2 * ta + tb] / r) ** 12
             assert abs(e[2 * k] - en) <= tol * ref_en + 1e-30, (trunc_name, k, e[2 * k], en)
