@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("HALMD_B200_LIB") or os.path.join(_HERE, "libhalmd_b20
 PLACEHOLDER = 0xFFFFFFFF
 LAYOUT_COLUMN, LAYOUT_ROW = 0, 1
 FORCE_POSITIONS_REDUCED = 0x100     # OR-ed into `layout` of the pair-force calls (include/halmd_b200.h)
-TRUNC_SHARP, TRUNC_SHIFTED, TRUNC_SMOOTH_R4 = 0, 1, 2
+TRUNC_SHARP, TRUNC_SHIFTED, TRUNC_SMOOTH_R4, TRUNC_FORCE_SHIFTED = 0, 1, 2, 3
 MAX_PAIR_TYPES = 16
 
 

@@ -154,7 +154,8 @@ class _lennard_jones:
         kind = type or kw.get("type") or "shifted"
         if cutoff is None:
             raise ValueError("truncate: missing argument 'cutoff'")
-        kinds = {"sharp": hx.TRUNC_SHARP, "shifted": hx.TRUNC_SHIFTED, "smooth_r4": hx.TRUNC_SMOOTH_R4}
+        kinds = {"sharp": hx.TRUNC_SHARP, "shifted": hx.TRUNC_SHIFTED, "smooth_r4": hx.TRUNC_SMOOTH_R4,
+                 "force_shifted": hx.TRUNC_FORCE_SHIFTED}
         if kind not in kinds:
             raise ValueError(f"truncate: truncation '{kind}' is not built (available: {sorted(kinds)})")
         if kind == "smooth_r4" and h is None:
