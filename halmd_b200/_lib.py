@@ -16,6 +16,7 @@ PLACEHOLDER = 0xFFFFFFFF
 LAYOUT_COLUMN, LAYOUT_ROW = 0, 1
 FORCE_POSITIONS_REDUCED = 0x100     # OR-ed into `layout` of the pair-force calls (include/halmd_b200.h)
 TRUNC_SHARP, TRUNC_SHIFTED, TRUNC_SMOOTH_R4, TRUNC_FORCE_SHIFTED = 0, 1, 2, 3
+CORR_MSD, CORR_MQD, CORR_VACF = 0, 1, 2
 MAX_PAIR_TYPES = 16
 
 
@@ -108,6 +109,7 @@ _protos = {
     "hx_sample_velocities": (C.c_int, [P, P, SZ, P, P]),
     "hx_msd_scratch_bytes": (SZ, [C.c_uint]),
     "hx_msd_block": (C.c_int, [P, P, C.c_uint, SZ, P, P, SZ, P]),
+    "hx_correlate_block": (C.c_int, [C.c_int, P, P, C.c_uint, SZ, P, P, SZ, P]),
     "hx_density_modes": (C.c_int, [P, SZ, P, C.c_uint, P, P]),
     "hx_thermodynamics": (C.c_int, [P, P, P, SZ, SZ, P, P]),
     "hx_ctl_reset": (C.c_int, [P, P]),

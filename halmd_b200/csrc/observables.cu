@@ -62,10 +62,30 @@ __device__ __forceinline__ wf wf_shfl_xor(wf a, int o)
     return b;
 }
 
+// inner_prod(a, b) in the order nvcc emits for the reference (cf. norm2 in common.cuh): fma(z, z', fma(x, x', y * y'))
+__device__ __forceinline__ float norm2_mixed(float4 a, float4 b)
+{
+    return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y)));
+}
+
 constexpr unsigned MSD_BLOCKS = 128;
 constexpr unsigned MSD_THREADS = 256;
 
+// correlation functions of two tagged-particle samples (halmd/observables/dynamics/*.hpp), evaluated in float
+//   HX_CORR_MSD   |r2 - r1|^2        mean_square_displacement.hpp:35-41
+//   HX_CORR_MQD   (|r2 - r1|^2)^2    mean_quartic_displacement.hpp:36-44
+//   HX_CORR_VACF  v1 . v2            velocity_autocorrelation.hpp:36-39
+template <int KIND>
+__device__ __forceinline__ float correlate(float4 a, float4 b)
+{
+    if (KIND == HX_CORR_VACF) return norm2_mixed(a, b);
+    float dx = __fsub_rn(b.x, a.x), dy = __fsub_rn(b.y, a.y), dz = __fsub_rn(b.z, a.z);
+    float rr = norm2(dx, dy, dz);
+    return KIND == HX_CORR_MQD ? __fmul_rn(rr, rr) : rr;
+}
+
 // grid = (MSD_BLOCKS, nlags): block accumulators → partial[(lag * MSD_BLOCKS + block)]
+template <int KIND>
 __global__ void k_msd_partial(const float4* __restrict__ first, const float4* const* __restrict__ samples, unsigned n,
                               wf* __restrict__ partial)
 {
@@ -73,10 +93,7 @@ __global__ void k_msd_partial(const float4* __restrict__ first, const float4* co
     const float4* second = samples[blockIdx.y];
     wf acc = {0., 0., 0.};
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 a = first[i], b = second[i];
-        // mean_square_displacement.hpp:35-41: dr = r2 - r1; inner_prod(dr, dr) in float
-        float dx = __fsub_rn(b.x, a.x), dy = __fsub_rn(b.y, a.y), dz = __fsub_rn(b.z, a.z);
-        wf_add(acc, static_cast<double>(norm2(dx, dy, dz)));
+        wf_add(acc, static_cast<double>(correlate<KIND>(first[i], second[i])));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -238,16 +255,27 @@ size_t hx_msd_scratch_bytes(unsigned nlags) { return static_cast<size_t>(nlags) 
 int hx_msd_block(const hx_float4* first_dev, const hx_float4* const* samples_dev, unsigned nlags, size_t nparticle,
                  double* out_dev, void* scratch_dev, size_t scratch_bytes, void* stream)
 {
+    return hx_correlate_block(HX_CORR_MSD, first_dev, samples_dev, nlags, nparticle, out_dev, scratch_dev, scratch_bytes, stream);
+}
+
+int hx_correlate_block(int kind, const hx_float4* first_dev, const hx_float4* const* samples_dev, unsigned nlags,
+                       size_t nparticle, double* out_dev, void* scratch_dev, size_t scratch_bytes, void* stream)
+{
     if (!first_dev || !samples_dev || !out_dev || !scratch_dev || nlags == 0 || nlags > 65535
-        || scratch_bytes < hx_msd_scratch_bytes(nlags) || nparticle >= 0x7FFFFFFFull) {
-        set_error("hx_msd_block: invalid argument");
+        || scratch_bytes < hx_msd_scratch_bytes(nlags) || nparticle >= 0x7FFFFFFFull || kind < HX_CORR_MSD
+        || kind > HX_CORR_VACF) {
+        set_error("hx_correlate_block: invalid argument");
         return HX_E_INVALID;
     }
     cudaStream_t st = as_stream(stream);
     wf* partial = static_cast<wf*>(scratch_dev);
-    k_msd_partial<<<dim3(MSD_BLOCKS, nlags), MSD_THREADS, 0, st>>>(
-        reinterpret_cast<const float4*>(first_dev), reinterpret_cast<const float4* const*>(samples_dev),
-        static_cast<unsigned>(nparticle), partial);
+    dim3 const grid(MSD_BLOCKS, nlags);
+    const float4* f = reinterpret_cast<const float4*>(first_dev);
+    const float4* const* sp = reinterpret_cast<const float4* const*>(samples_dev);
+    unsigned const n = static_cast<unsigned>(nparticle);
+    if (kind == HX_CORR_MSD) k_msd_partial<HX_CORR_MSD><<<grid, MSD_THREADS, 0, st>>>(f, sp, n, partial);
+    else if (kind == HX_CORR_MQD) k_msd_partial<HX_CORR_MQD><<<grid, MSD_THREADS, 0, st>>>(f, sp, n, partial);
+    else k_msd_partial<HX_CORR_VACF><<<grid, MSD_THREADS, 0, st>>>(f, sp, n, partial);
     int rc = check_launch("k_msd_partial");
     if (rc) return rc;
     k_msd_final<<<nlags, 32, 0, st>>>(partial, MSD_BLOCKS, out_dev);

@@ -268,6 +268,14 @@ size_t hx_msd_scratch_bytes(unsigned nlags);
 int hx_msd_block(const hx_float4* first_dev, const hx_float4* const* samples_dev, unsigned nlags,
                  size_t nparticle, double* out_dev, void* scratch_dev, size_t scratch_bytes,
                  void* stream);
+/* the same accumulation for the other tagged-particle correlation functions of halmd/observables/dynamics:
+ * HX_CORR_MSD |dr|^2, HX_CORR_MQD |dr|^4 (mean_quartic_displacement.hpp:36-44), HX_CORR_VACF v1.v2 on velocity
+ * samples (velocity_autocorrelation.hpp:36-39); scratch as for hx_msd_block */
+#define HX_CORR_MSD 0
+#define HX_CORR_MQD 1
+#define HX_CORR_VACF 2
+int hx_correlate_block(int kind, const hx_float4* first_dev, const hx_float4* const* samples_dev, unsigned nlags,
+                       size_t nparticle, double* out_dev, void* scratch_dev, size_t scratch_bytes, void* stream);
 /* rho_dev[2*q + {0,1}] = (sum cos q.r, -sum sin q.r) as doubles; q_dev: float[3*nq] */
 int hx_density_modes(const hx_float4* position_hi_dev, size_t nparticle, const float* q_dev,
                      unsigned nq, double* rho_dev, void* stream);

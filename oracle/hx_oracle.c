@@ -707,6 +707,29 @@ void oracle_msd(const f4* first, const f4* second, size_t n, double out[3])
     out[0] = cnt; out[1] = m; out[2] = v;
 }
 
+/* the other tagged-particle correlation functions, same accumulation: kind 1 mean_quartic_displacement.hpp:36-44,
+ * kind 2 velocity_autocorrelation.hpp:36-39 (kind 0 = oracle_msd) */
+void oracle_correlate(int kind, const f4* first, const f4* second, size_t n, double out[3])
+{
+    double cnt = 0, m = 0, v = 0;
+    for (size_t i = 0; i < n; ++i) {
+        float val;
+        if (kind == 2) {
+            val = fmaf(first[i].z, second[i].z, fmaf(first[i].x, second[i].x, first[i].y * second[i].y));
+        } else {
+            float dx = second[i].x - first[i].x, dy = second[i].y - first[i].y, dz = second[i].z - first[i].z;
+            float rr = norm2(dx, dy, dz);
+            val = kind == 1 ? rr * rr : rr;
+        }
+        double x = (double)val;
+        double t = x - m;
+        cnt += 1;
+        m += t / cnt;
+        v += t * (x - m);
+    }
+    out[0] = cnt; out[1] = m; out[2] = v;
+}
+
 /* density_mode_kernel.cu:46-80 + density_mode.cpp:126-129: (sum cos, -sum sin), summed in double here */
 void oracle_density_modes(const f4* pos, size_t n, const float* q, unsigned nq, double* rho)
 {

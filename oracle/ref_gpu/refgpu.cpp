@@ -26,7 +26,9 @@
 #include <halmd/mdsim/gpu/sorts/hilbert_kernel.hpp>
 #include <halmd/algorithm/gpu/reduce_kernel.hpp>
 #include <halmd/numeric/accumulator.hpp>
+#include <halmd/observables/dynamics/mean_quartic_displacement.hpp>
 #include <halmd/observables/dynamics/mean_square_displacement.hpp>
+#include <halmd/observables/dynamics/velocity_autocorrelation.hpp>
 #include <halmd/observables/gpu/density_mode_kernel.hpp>
 #include <halmd/observables/gpu/dynamics/tagged_particle.hpp>
 
@@ -514,4 +516,42 @@ extern "C" int refgpu_msd(const float* first4, const float* second4, size_t npar
     out[1] = static_cast<double>(mean(total()));
     out[2] = static_cast<double>(variance(total()));
     return 0;
+}
+
+namespace {
+
+template <typename correlation_function>
+int reduce_correlation(const float* first4, const float* second4, size_t nparticle, double out[3])
+{
+    typedef observables::gpu::dynamics::tagged_particle<correlation_function, dsfloat> acc_type;
+    unsigned const blocks = 32, threads = 256;
+    dbuf<float4> d_a(reinterpret_cast<const float4*>(first4), nparticle), d_b(reinterpret_cast<const float4*>(second4), nparticle);
+    dbuf<acc_type> d_block(blocks);
+    if (!d_a.p || !d_b.p || !d_block.p) return static_cast<int>(cudaErrorMemoryAllocation);
+    auto& kernel = reduction_kernel<acc_type>::kernel;
+    RG_TRY(
+        kernel.reduce.configure(dim3(blocks), dim3(threads));
+        typename acc_type::iterator first(std::make_tuple(static_cast<float4 const*>(d_a.p), static_cast<float4 const*>(d_b.p)));
+        kernel.reduce(first, static_cast<std::ptrdiff_t>(nparticle), d_block.p, acc_type());
+    )
+    RG_CHECK(cudaDeviceSynchronize());
+    std::vector<acc_type> h(blocks);
+    RG_CHECK(static_cast<cudaError_t>(d_block.down(h.data())));
+    acc_type total;
+    for (unsigned i = 0; i < blocks; ++i) total(h[i]);
+    out[0] = static_cast<double>(count(total()));
+    out[1] = static_cast<double>(mean(total()));
+    out[2] = static_cast<double>(variance(total()));
+    return 0;
+}
+
+} // namespace
+
+// mean_quartic_displacement_kernel.cu / velocity_autocorrelation_kernel.cu: the same reduction as refgpu_msd with the
+// other two tagged-particle correlation functions (kind 1 / 2)
+extern "C" int refgpu_correlate(int kind, const float* first4, const float* second4, size_t nparticle, double out[3])
+{
+    if (kind == 1) return reduce_correlation<observables::dynamics::mean_quartic_displacement<3, float>>(first4, second4, nparticle, out);
+    if (kind == 2) return reduce_correlation<observables::dynamics::velocity_autocorrelation<3, float>>(first4, second4, nparticle, out);
+    return reduce_correlation<observables::dynamics::mean_square_displacement<3, float>>(first4, second4, nparticle, out);
 }
