@@ -187,6 +187,8 @@ _module_protos = {
     "hxm_blocking_finalise": (C.c_int, [P]),
     "hxm_blocking_msd": (C.c_int, [P, D3]),
     "hxm_blocking_isf": (C.c_int, [P, D3]),
+    "hxm_blocking_mqd": (C.c_int, [P, D3]),
+    "hxm_blocking_vacf": (C.c_int, [P, D3]),
     "hxm_core_run_sampling": (C.c_int, [P, U64, P]),
 }
 MODULE_SYMBOLS = tuple(_module_protos)

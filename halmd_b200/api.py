@@ -613,6 +613,12 @@ class _blocking_scheme(_Handle):
     def mean_square_displacement(self):
         return self._result(lib.hxm_blocking_msd, ())
 
+    def mean_quartic_displacement(self):
+        return self._result(lib.hxm_blocking_mqd, ())
+
+    def velocity_autocorrelation(self):
+        return self._result(lib.hxm_blocking_vacf, ())
+
     def intermediate_scattering_function(self):
         if self.wavevector is None:
             raise HxError("blocking_scheme: no wavevector module given")

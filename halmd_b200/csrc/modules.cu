@@ -514,9 +514,10 @@ struct hxm_core {
 struct hxm_blocking {
     struct sample {
         float4* positions = nullptr;         // unfolded positions in id order (device)
+        float4* velocities = nullptr;        // velocities in id order (device)
         std::vector<double> rho;             // density modes (re, im) per wavevector
         uint64_t step = 0;
-        ~sample() { if (positions) cudaFree(positions); }
+        ~sample() { if (positions) cudaFree(positions); if (velocities) cudaFree(velocities); }
     };
     hxm_core* core = nullptr;
     unsigned block_size = 10, separation = 10;
@@ -525,6 +526,7 @@ struct hxm_blocking {
     std::shared_ptr<sample> current;         // sample acquired at the current step (shared between levels)
     // correlations
     std::vector<welford> msd;                // [level][lag]
+    std::vector<welford> mqd, vacf;          // [level][lag]: mean-quartic displacement, velocity autocorrelation
     std::vector<welford> isf;                // [level][lag][shell]
     unsigned nq = 0, nshell = 0;
     std::vector<unsigned> shell_offsets;
@@ -552,6 +554,9 @@ struct hxm_blocking {
         float* Lf = core->integrator->Lf;
         HXM_TRY(hx_sample_positions(reinterpret_cast<hx_float4*>(p->pos), reinterpret_cast<hx_float4*>(p->image), p->rid, p->n,
                                     Lf, reinterpret_cast<hx_float4*>(s->positions), p->st));
+        HXM_TRY(dev_alloc(&s->velocities, p->n));
+        HXM_TRY(hx_sample_velocities(reinterpret_cast<hx_float4*>(p->vel), p->rid, p->n,
+                                     reinterpret_cast<hx_float4*>(s->velocities), p->st));
         if (nq > 0) {
             HXM_TRY(hx_density_modes(reinterpret_cast<hx_float4*>(p->pos), p->n, d_q, nq, d_rho, p->st));
             s->rho.resize(2 * nq);
@@ -584,6 +589,24 @@ struct hxm_blocking {
                 welford w;
                 w.n = h[3 * k]; w.m = h[3 * k + 1]; w.v = h[3 * k + 2];
                 welford_merge(msd[level * block_size + k], w);
+            }
+            // mean-quartic displacement on the same samples, velocity autocorrelation on the velocity samples
+            for (int kind = HX_CORR_MQD; kind <= HX_CORR_VACF; ++kind) {
+                if (kind == HX_CORR_VACF) {
+                    for (unsigned k = 0; k < nl; ++k) ptrs[k] = block[k]->velocities;
+                    HXM_CUDA(cudaMemcpyAsync(d_ptrs, ptrs.data(), nl * sizeof(float4*), cudaMemcpyHostToDevice, p->st));
+                }
+                HXM_TRY(hx_correlate_block(kind, reinterpret_cast<const hx_float4*>(ptrs[0]),
+                                           reinterpret_cast<const hx_float4* const*>(d_ptrs), nl, p->n, d_msd, d_msd_scratch,
+                                           msd_scratch_bytes, p->st));
+                HXM_CUDA(cudaMemcpyAsync(h.data(), d_msd, 3 * nl * sizeof(double), cudaMemcpyDeviceToHost, p->st));
+                HXM_CUDA(cudaStreamSynchronize(p->st));
+                auto& acc = kind == HX_CORR_MQD ? mqd : vacf;
+                for (unsigned k = 0; k < nl; ++k) {
+                    welford w;
+                    w.n = h[3 * k]; w.m = h[3 * k + 1]; w.v = h[3 * k + 2];
+                    welford_merge(acc[level * block_size + k], w);
+                }
             }
             if (nq > 0) {
                 // intermediate_scattering_function.hpp:90-113
@@ -1165,6 +1188,8 @@ int hxm_blocking_create(hxm_core* core, double max_lag_time, double resolution, 
     b->origin.assign(levels, core->step);
     b->blocks.resize(levels);
     b->msd.assign(levels * block_size, welford());
+    b->mqd.assign(levels * block_size, welford());
+    b->vacf.assign(levels * block_size, welford());
     hxm_particle* p = core->integrator->particle;
     b->norm = static_cast<double>(p->n);
     b->nq = nq;
@@ -1211,6 +1236,20 @@ int hxm_blocking_msd(hxm_blocking* b, double* out)
 {
     if (!b || !out) return HX_E_INVALID;
     for (size_t i = 0; i < b->msd.size(); ++i) { out[3 * i] = b->msd[i].n; out[3 * i + 1] = b->msd[i].m; out[3 * i + 2] = b->msd[i].v; }
+    return 0;
+}
+
+int hxm_blocking_mqd(hxm_blocking* b, double* out)
+{
+    if (!b || !out) return HX_E_INVALID;
+    for (size_t i = 0; i < b->mqd.size(); ++i) { out[3 * i] = b->mqd[i].n; out[3 * i + 1] = b->mqd[i].m; out[3 * i + 2] = b->mqd[i].v; }
+    return 0;
+}
+
+int hxm_blocking_vacf(hxm_blocking* b, double* out)
+{
+    if (!b || !out) return HX_E_INVALID;
+    for (size_t i = 0; i < b->vacf.size(); ++i) { out[3 * i] = b->vacf[i].n; out[3 * i + 1] = b->vacf[i].m; out[3 * i + 2] = b->vacf[i].v; }
     return 0;
 }
 

@@ -160,6 +160,10 @@ int hxm_blocking_finalise(hxm_blocking* b);
 /* results: (count, mean, M2) per [level][lag] for MSD; per [level][lag][shell] for ISF */
 int hxm_blocking_msd(hxm_blocking* b, double* out);
 int hxm_blocking_isf(hxm_blocking* b, double* out);
+/* observables.dynamics.mean_quartic_displacement / velocity_autocorrelation on the same blocking scheme:
+ * out[(level * block_size + lag) * 3 + {0,1,2}] = (count, mean, M2) like hxm_blocking_msd */
+int hxm_blocking_mqd(hxm_blocking* b, double* out);
+int hxm_blocking_vacf(hxm_blocking* b, double* out);
 /* run `steps` steps sampling the blocking scheme at every step that a level is due (sampler on_sample slot) */
 int hxm_core_run_sampling(hxm_core* c, uint64_t steps, hxm_blocking* b);
 

@@ -303,7 +303,9 @@ def test_blocking_scheme_msd_and_isf(api):
         unfolded[ids] = (img.astype(np.float64) * L.astype(np.float32).astype(np.float64) + r.astype(np.float64)).astype(np.float32)
         wrapped = np.zeros((n, 3), dtype=np.float32)
         wrapped[ids] = r
-        return unfolded, wrapped
+        vel = np.zeros((n, 3), dtype=np.float32)
+        vel[ids] = p.get("velocity").astype(np.float32)
+        return unfolded, wrapped, vel
 
     due = sorted({st for _, blk in events for st in blk})
     for k in range(steps + 1):
@@ -323,7 +325,9 @@ def test_blocking_scheme_msd_and_isf(api):
     exp_isf_cnt = np.zeros((nlev, 5, len(wv.shell)))
     q = wv.value.astype(np.float32)
     rho = {}
-    for st, (unf, wr) in record.items():
+    exp_mqd = np.zeros((nlev, 5))
+    exp_vacf = np.zeros((nlev, 5))
+    for st, (unf, wr, _) in record.items():
         qr = wr.astype(np.float64) @ q.astype(np.float64).T
         rho[st] = np.stack([np.cos(qr).sum(axis=0), -np.sin(qr).sum(axis=0)], axis=1)
     for lev, blk in events:
@@ -332,6 +336,8 @@ def test_blocking_scheme_msd_and_isf(api):
             d = record[st][0].astype(np.float64) - first
             exp_cnt[lev, lag] += n
             exp_sum[lev, lag] += (d ** 2).sum()
+            exp_mqd[lev, lag] += ((d ** 2).sum(axis=1) ** 2).sum()
+            exp_vacf[lev, lag] += (record[blk[0]][2].astype(np.float64) * record[st][2].astype(np.float64)).sum()
             for si, (a, b) in enumerate(wv.shell):
                 re = (rho[blk[0]][a:b, 0] * rho[st][a:b, 0] + rho[blk[0]][a:b, 1] * rho[st][a:b, 1]) / n
                 exp_isf[lev, lag, si] += re.sum()
@@ -340,6 +346,11 @@ def test_blocking_scheme_msd_and_isf(api):
     nz = exp_cnt > 0
     assert np.allclose(msd["mean"][nz], (exp_sum / np.maximum(exp_cnt, 1))[nz], rtol=1e-5, atol=1e-9)
     assert np.all(msd["mean"][:, 0][exp_cnt[:, 0] > 0] == 0)
+    mqd, vacf = bs.mean_quartic_displacement(), bs.velocity_autocorrelation()
+    assert np.array_equal(mqd["count"], exp_cnt) and np.array_equal(vacf["count"], exp_cnt)
+    assert np.allclose(mqd["mean"][nz], (exp_mqd / np.maximum(exp_cnt, 1))[nz], rtol=1e-5, atol=1e-12)
+    assert np.allclose(vacf["mean"][nz], (exp_vacf / np.maximum(exp_cnt, 1))[nz], rtol=1e-5, atol=1e-7)
+    assert np.all(vacf["mean"][:, 0][exp_cnt[:, 0] > 0] > 1.0)            # <v^2> = 3 T at lag 0 (T ~ 0.7 after melting)
     assert np.array_equal(isf["count"], exp_isf_cnt)
     nz = exp_isf_cnt > 0
     assert np.allclose(isf["mean"][nz], (exp_isf / np.maximum(exp_isf_cnt, 1))[nz], rtol=2e-4, atol=2e-4)
