@@ -56,12 +56,26 @@ def test_host_side_plans_match_oracle(hx, oracle):
 
 def test_potential_tables_match_oracle(hx, oracle):
     eps, sigma, cut = [1.0, 1.5, 1.5, 0.5], [1.0, 0.8, 0.8, 0.88], [2.5] * 4
-    for trunc, h in ((0, 0.0), (1, 0.0), (2, 0.005)):
+    for trunc, h in ((0, 0.0), (1, 0.0), (2, 0.005), (3, 0.0)):
         p = hx.LjParams()
         hx.check(hx.lib.hx_potential_lj_init(C.byref(p), 2, 2, hx.farr(eps), hx.farr(sigma), trunc, hx.farr(cut), h))
         q = support.OLjParams()
         oracle.oracle_lj_init(C.byref(q), 2, 2, support.farr(eps), support.farr(sigma), trunc, support.farr(cut), C.c_float(h))
         assert bytes(p) == bytes(q)
+
+
+def test_planar_wall_tables_match_oracle(hx):
+    """hx_planar_wall_init (host code in the product library) against the test-side restatement of
+    planar_wall.cpp:83-112, with the parameters of the reference's unit test."""
+    a = support.REF_WALL
+    w = hx.PlanarWall()
+    f32 = lambda v: hx.farr(np.asarray(v, dtype=np.float32).reshape(-1))      # noqa: E731
+    hx.check(hx.lib.hx_planar_wall_init(C.byref(w), 3, 2, f32(a["offset"]), f32(a["surface_normal"]), f32(a["epsilon"]),
+                                        f32(a["sigma"]), f32(a["wetting"]), f32(a["cutoff"]), a["smoothing"]))
+    assert bytes(w) == bytes(support.make_oracle_wall(**a))
+    assert hx.lib.hx_planar_wall_init(C.byref(w), 9, 1, f32([0] * 9), f32([[1, 0, 0]] * 9), f32([1] * 9), f32([1] * 9),
+                                      f32([1] * 9), f32([1] * 9), 0.01) < 0
+    assert hx.lib.hx_planar_wall_init(C.byref(w), 1, 1, f32([0]), f32([[0, 0, 0]]), f32([1]), f32([1]), f32([1]), f32([1]), 0.01) < 0
 
 
 def test_contract_violations_return_error_codes(hx):
