@@ -101,6 +101,8 @@ _protos = {
     "hx_rand48_seed": (C.c_int, [C.POINTER(Rand48), C.c_uint, C.c_uint, C.c_uint, P, P]),
     "hx_rand48_uniform": (C.c_int, [C.POINTER(Rand48), P, P, SZ, P]),
     "hx_andersen_finalize": (C.c_int, [P, P, SZ, SZ, C.c_float, C.c_float, C.c_float, C.POINTER(Rand48), P, P]),
+    "hx_hoover_integrate": (C.c_int, [P, P, P, P, SZ, C.c_float, C.c_double, F3, P]),
+    "hx_hoover_rescale": (C.c_int, [P, SZ, C.c_double, P]),
     "hx_andersen_scratch_bytes": (SZ, [SZ]),
     "hx_andersen_finalize2": (C.c_int, [P, P, SZ, SZ, C.c_float, C.c_float, C.c_float, C.POINTER(Rand48), P, P, SZ, P, P]),
     "hx_andersen_finalize_guarded": (C.c_int, [P, P, SZ, SZ, C.c_float, C.c_float, C.c_float,
@@ -170,6 +172,9 @@ _module_protos = {
     "hxm_integrator_finalize": (C.c_int, [P]),
     "hxm_integrator_set_timestep": (C.c_int, [P, C.c_double]),
     "hxm_integrator_set_temperature": (C.c_int, [P, C.c_double]),
+    "hxm_integrator_hoover_create": (C.c_int, [P, P, D3, C.c_double, C.c_double, C.c_double, PP]),
+    "hxm_integrator_hoover_state": (C.c_int, [P, C.POINTER(C.c_double)]),
+    "hxm_integrator_hoover_set_mass": (C.c_int, [P, C.POINTER(C.c_double)]),
     "hxm_core_create": (C.c_int, [P, PP]),
     "hxm_core_destroy": (None, [P]),
     "hxm_core_mdstep": (C.c_int, [P]),

@@ -393,6 +393,39 @@ class _verlet_nvt_andersen(_integrator):
         self.temperature = float(temperature)
 
 
+class _verlet_nvt_hoover(_integrator):
+    """mdsim.integrators.verlet_nvt_hoover (lua/halmd/mdsim/integrators/verlet_nvt_hoover.lua.in:57-61): Nosé–Hoover
+    chain of length 2; `position`, `velocity`, `mass` are the chain variables, `internal_energy` the chain's energy
+    per particle, so that E_tot + internal_energy is conserved."""
+
+    def __init__(self, box=None, particle=None, timestep=0.001, temperature=1.0, resonance_frequency=5.0, force=None):
+        super().__init__()
+        force = force or _find_force(particle)
+        self.box, self.particle, self.force, self.timestep = box, particle, force, float(timestep)
+        self.temperature, self.resonance_frequency = float(temperature), float(resonance_frequency)
+        check(lib.hxm_integrator_hoover_create(particle._h, force._h, box._d3(), float(timestep), float(temperature),
+                                               float(resonance_frequency), C.byref(self._h)),
+              "integrators.verlet_nvt_hoover")
+        core._register(self)
+
+    def _state(self):
+        out = (C.c_double * 7)()
+        check(lib.hxm_integrator_hoover_state(self._h, out), "integrators.verlet_nvt_hoover")
+        return list(out)
+
+    position = property(lambda self: self._state()[0:2])
+    velocity = property(lambda self: self._state()[2:4])
+    mass = property(lambda self: self._state()[4:6])
+    internal_energy = property(lambda self: self._state()[6])
+
+    def set_temperature(self, temperature):
+        check(lib.hxm_integrator_set_temperature(self._h, float(temperature)))
+        self.temperature = float(temperature)
+
+    def set_mass(self, mass):
+        check(lib.hxm_integrator_hoover_set_mass(self._h, (C.c_double * 2)(*map(float, mass))))
+
+
 # ---- mdsim.core + observables.sampler ------------------------------------------------------------------------------------------
 class _core(_Handle):
     _destroy = "hxm_core_destroy"
@@ -641,7 +674,7 @@ mdsim = _NS(
     box=box, particle=particle, binning=binning, neighbour=neighbour, core=core,
     potentials=_NS(pair=_NS(lennard_jones=_lennard_jones), external=_NS(planar_wall=_planar_wall)),
     forces=_NS(pair=_pair, external=_external_force),
-    integrators=_NS(verlet=_verlet, verlet_nvt_andersen=_verlet_nvt_andersen),
+    integrators=_NS(verlet=_verlet, verlet_nvt_andersen=_verlet_nvt_andersen, verlet_nvt_hoover=_verlet_nvt_hoover),
 )
 
 observables = _NS(

@@ -271,6 +271,71 @@ __global__ void k_andersen_finalize(float4* __restrict__ vel, const float4* __re
     r48_unpack(g.s, state + 3 * t);
 }
 
+// Double-single product with both low words live, contracted as nvcc --fmad=true contracts dsmul (dsfun.hpp:178-207)
+// in the reference build: the Dekker splits and the partial products ride on FFMA, only a0 * b0 is rounded on its own.
+__device__ __forceinline__ ds ds_mul_contracted(ds a, ds b)
+{
+    float const sa1 = __fmaf_rn(a.hi, 8193.0f, -__fmaf_rn(a.hi, 8193.0f, -a.hi));
+    float const sb1 = __fmaf_rn(b.hi, 8193.0f, -__fmaf_rn(b.hi, 8193.0f, -b.hi));
+    float const sa2 = __fsub_rn(a.hi, sa1);
+    float const sb2 = __fsub_rn(b.hi, sb1);
+    float const c11 = __fmul_rn(a.hi, b.hi);
+    float c21 = __fmaf_rn(sa1, sb1, -c11);
+    c21 = __fmaf_rn(sa1, sb2, c21);
+    c21 = __fmaf_rn(sb1, sa2, c21);
+    c21 = __fmaf_rn(sa2, sb2, c21);
+    float const c2 = __fmaf_rn(a.hi, b.lo, __fmul_rn(a.lo, b.hi));
+    float const t1 = __fadd_rn(c11, c2);
+    float const e = __fsub_rn(t1, c11);
+    float t2 = __fadd_rn(__fsub_rn(c2, e), __fsub_rn(c11, __fsub_rn(t1, e)));
+    t2 = __fmaf_rn(a.lo, b.lo, __fadd_rn(c21, t2));
+    ds c;
+    c.hi = __fadd_rn(t1, t2);
+    c.lo = __fsub_rn(t2, __fsub_rn(c.hi, t1));
+    return c;
+}
+
+// ---- Nose-Hoover chain (verlet_nvt_hoover_kernel.cu:37-125) -------------------------------------------------------------
+// integrate: v *= scale (double-single product), then the velocity-Verlet first half-step; rescale: v *= scale.
+// The chain variables live on the host (verlet_nvt_hoover.cpp:185-222); finalize is the plain Verlet half-kick.
+__global__ void __launch_bounds__(128) k_hoover_integrate(float4* __restrict__ pos, float4* __restrict__ image,
+                                                         float4* __restrict__ vel, const float4* __restrict__ force,
+                                                         unsigned A, float dt, ds scale, vec3 L)
+{
+    unsigned const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A) return;
+    float4 vh = vel[i], vl = vel[i + A];
+    float4 const f = force[i];
+    float const mass = vh.w;
+    ds3 v = {ds_mul_contracted(make_ds(vh.x, vl.x), scale), ds_mul_contracted(make_ds(vh.y, vl.y), scale),
+             ds_mul_contracted(make_ds(vh.z, vl.z), scale)};
+    half_kick(v, f, __fmul_rn(dt, 0.5f), mass);
+    float4 const ph = pos[i], pl = pos[i + A];
+    ds rx = make_ds(ph.x, pl.x), ry = make_ds(ph.y, pl.y), rz = make_ds(ph.z, pl.z);
+    float const ix = drift_wrap(rx, v.x, dt, L.x);
+    float const iy = drift_wrap(ry, v.y, dt, L.y);
+    float const iz = drift_wrap(rz, v.z, dt, L.z);
+    pos[i] = make_float4(rx.hi, ry.hi, rz.hi, ph.w);
+    pos[i + A] = make_float4(rx.lo, ry.lo, rz.lo, 0.f);
+    vel[i] = make_float4(v.x.hi, v.y.hi, v.z.hi, mass);
+    vel[i + A] = make_float4(v.x.lo, v.y.lo, v.z.lo, 0.f);
+    if (!(ix == 0.f && iy == 0.f && iz == 0.f)) {
+        float4 const im = image[i];
+        image[i] = make_float4(__fadd_rn(ix, im.x), __fadd_rn(iy, im.y), __fadd_rn(iz, im.z), 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_hoover_rescale(float4* __restrict__ vel, unsigned A, ds scale)
+{
+    unsigned const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A) return;
+    float4 const vh = vel[i], vl = vel[i + A];
+    ds const x = ds_mul_contracted(make_ds(vh.x, vl.x), scale), y = ds_mul_contracted(make_ds(vh.y, vl.y), scale),
+             z = ds_mul_contracted(make_ds(vh.z, vl.z), scale);
+    vel[i] = make_float4(x.hi, y.hi, z.hi, vh.w);
+    vel[i + A] = make_float4(x.lo, y.lo, z.lo, 0.f);
+}
+
 // ---- Andersen thermostat in two passes --------------------------------------------------------------------------------
 // The reference kernel above is sequential by construction: 8192 generator threads walk the particle array with a
 // grid stride, and what a thread draws at one particle depends on the collisions of its warp at all earlier ones
@@ -549,6 +614,42 @@ static int andersen_launch(hx_float4* velocity_dev, const hx_float4* force_dev, 
         static_cast<unsigned>(nparticle), static_cast<unsigned>(array_size), timestep, sqrt_temperature, q, state_dev,
         r48_pack(rng->a), r48_pack(rng->c), ctl);
     return check_launch("k_andersen_finalize");
+}
+
+// double -> double-single as halmd::dsfloat(double) does (numeric/mp/dsfloat.hpp: hi = float(a), lo = float(a - hi))
+static ds ds_from_double(double a)
+{
+    ds r;
+    r.hi = static_cast<float>(a);
+    r.lo = static_cast<float>(a - static_cast<double>(r.hi));
+    return r;
+}
+
+int hx_hoover_integrate(hx_float4* position_dev, hx_float4* image_dev, hx_float4* velocity_dev, const hx_float4* force_dev,
+                        size_t array_size, float timestep, double scale, const float box_length[3], void* stream)
+{
+    if (!position_dev || !image_dev || !velocity_dev || !force_dev || !box_length || array_size == 0
+        || array_size >= 0x7FFFFFFFull) {
+        set_error("hx_hoover_integrate: invalid argument");
+        return HX_E_INVALID;
+    }
+    k_hoover_integrate<<<div_up(array_size, 128), 128, 0, as_stream(stream)>>>(
+        reinterpret_cast<float4*>(position_dev), reinterpret_cast<float4*>(image_dev), reinterpret_cast<float4*>(velocity_dev),
+        reinterpret_cast<const float4*>(force_dev), static_cast<unsigned>(array_size), timestep, ds_from_double(scale),
+        make_vec3(box_length));
+    return check_launch("k_hoover_integrate");
+}
+
+int hx_hoover_rescale(hx_float4* velocity_dev, size_t array_size, double scale, void* stream)
+{
+    if (!velocity_dev || array_size == 0 || array_size >= 0x7FFFFFFFull) {
+        set_error("hx_hoover_rescale: invalid argument");
+        return HX_E_INVALID;
+    }
+    k_hoover_rescale<<<div_up(array_size, 128), 128, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(velocity_dev),
+                                                                            static_cast<unsigned>(array_size),
+                                                                            ds_from_double(scale));
+    return check_launch("k_hoover_rescale");
 }
 
 size_t hx_andersen_scratch_bytes(size_t nparticle)

@@ -338,7 +338,7 @@ struct hxm_force {
 
 // ---- integrators -------------------------------------------------------------------------------------------------------------
 struct hxm_integrator {
-    enum kind_t { VERLET, ANDERSEN } kind = VERLET;
+    enum kind_t { VERLET, ANDERSEN, HOOVER } kind = VERLET;
     hxm_particle* particle = nullptr;
     hxm_force* force = nullptr;
     float Lf[3];
@@ -349,8 +349,52 @@ struct hxm_integrator {
     hx_rand48 rng;
     uint16_t* rng_state = nullptr;
     unsigned char* andersen_scratch = nullptr;
+    // Nose-Hoover chain (verlet_nvt_hoover.hpp:100-160): chain positions / velocities / masses, derived time steps
+    double xi[2] = {0, 0}, v_xi[2] = {0, 0}, mass_xi[2] = {1, 1};
+    double resonance_frequency = 5, en_kin_target_2 = 0, en_nhc = 0;
+    double* d_hoover = nullptr;      // device / pinned scratch of the kinetic-energy reduction
+    double* h_hoover = nullptr;
 
-    ~hxm_integrator() { dev_free(rng_state); dev_free(andersen_scratch); }
+    ~hxm_integrator()
+    {
+        dev_free(rng_state); dev_free(andersen_scratch); dev_free(d_hoover);
+        if (h_hoover) cudaFreeHost(h_hoover);
+    }
+
+    // verlet_nvt_hoover::set_temperature (verlet_nvt_hoover.cpp:79-95): masses after Martyna et al.
+    void update_hoover()
+    {
+        double const dof = 3.0 * static_cast<double>(particle->n);
+        en_kin_target_2 = dof * temperature;
+        double const omega_sq = std::pow(2 * M_PI * resonance_frequency, 2);
+        mass_xi[0] = dof * temperature / omega_sq;
+        mass_xi[1] = temperature / omega_sq;
+    }
+
+    // verlet_nvt_hoover::propagate_chain (verlet_nvt_hoover.cpp:185-222): returns the velocity scale factor
+    int propagate_chain(double* scale)
+    {
+        hxm_particle* p = particle;
+        HXM_TRY(hx_thermodynamics(reinterpret_cast<hx_float4*>(p->vel), nullptr, nullptr, p->A, p->n, d_hoover, p->st));
+        HXM_CUDA(cudaMemcpyAsync(h_hoover, d_hoover, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->st));
+        HXM_CUDA(cudaStreamSynchronize(p->st));
+        double en_kin_2 = h_hoover[0];          // sum m v^2 = 2 E_kin
+        double const dt4 = timestep / 4, dt8 = timestep / 8, dt2 = timestep / 2;
+        v_xi[1] += (mass_xi[0] * v_xi[0] * v_xi[0] - temperature) / mass_xi[1] * dt4;
+        double const t = std::exp(-v_xi[1] * dt8);
+        v_xi[0] *= t;
+        v_xi[0] += (en_kin_2 - en_kin_target_2) / mass_xi[0] * dt4;
+        v_xi[0] *= t;
+        for (int i = 0; i < 2; ++i) xi[i] += v_xi[i] * dt2;
+        double const s = std::exp(-v_xi[0] * dt2);
+        en_kin_2 *= s * s;
+        v_xi[0] *= t;
+        v_xi[0] += (en_kin_2 - en_kin_target_2) / mass_xi[0] * dt4;
+        v_xi[0] *= t;
+        v_xi[1] += (mass_xi[0] * v_xi[0] * v_xi[0] - temperature) / mass_xi[1] * dt4;
+        *scale = s;
+        return 0;
+    }
 
     void update_andersen()
     {
@@ -363,6 +407,17 @@ struct hxm_integrator {
     {
         hxm_particle* p = particle;
         HXM_TRY(force->ensure(false));      // read_cache(particle->force()) before invalidating the positions
+        if (kind == HOOVER) {
+            // verlet_nvt_hoover::integrate (verlet_nvt_hoover.cpp:103-135)
+            double scale = 1;
+            HXM_TRY(propagate_chain(&scale));
+            HXM_TRY(hx_hoover_integrate(reinterpret_cast<hx_float4*>(p->pos), reinterpret_cast<hx_float4*>(p->image),
+                                        reinterpret_cast<hx_float4*>(p->vel), reinterpret_cast<hx_float4*>(p->force), p->A,
+                                        static_cast<float>(timestep), scale, Lf, p->st));
+            p->pos_ver++;
+            p->reduced = true;
+            return 0;
+        }
         HXM_TRY(hx_verlet_integrate(reinterpret_cast<hx_float4*>(p->pos), reinterpret_cast<hx_float4*>(p->image),
                                     reinterpret_cast<hx_float4*>(p->vel), reinterpret_cast<hx_float4*>(p->force), p->A,
                                     static_cast<float>(timestep), Lf, p->st));
@@ -374,6 +429,19 @@ struct hxm_integrator {
     int finalize_kernel(uint32_t* ctl)
     {
         hxm_particle* p = particle;
+        if (kind == HOOVER) {
+            // verlet_nvt_hoover::finalize (verlet_nvt_hoover.cpp:140-183): half-kick, chain, rescale, chain energy
+            HXM_TRY(hx_verlet_finalize(reinterpret_cast<hx_float4*>(p->vel), reinterpret_cast<hx_float4*>(p->force), p->A,
+                                       static_cast<float>(timestep), p->st));
+            double scale = 1;
+            HXM_TRY(propagate_chain(&scale));
+            HXM_TRY(hx_hoover_rescale(reinterpret_cast<hx_float4*>(p->vel), p->A, scale, p->st));
+            double const N = static_cast<double>(p->n);
+            en_nhc = temperature * (3.0 * N * xi[0] + xi[1]);
+            for (int i = 0; i < 2; ++i) en_nhc += mass_xi[i] * v_xi[i] * v_xi[i] / 2;
+            en_nhc /= N;
+            return 0;
+        }
         if (kind == VERLET) {
             if (ctl) return hx_verlet_finalize_guarded(reinterpret_cast<hx_float4*>(p->vel), reinterpret_cast<hx_float4*>(p->force),
                                                        p->A, static_cast<float>(timestep), ctl, p->st);
@@ -431,6 +499,12 @@ struct hxm_core {
         // float(r_skin / 2) as compared in from_binning.cpp:130-131
         float const skin_half = static_cast<float>(nb->r_skin / 2);
         bool const fuse = (in->kind == hxm_integrator::VERLET);
+        if (in->kind == hxm_integrator::HOOVER) {
+            // the chain is propagated on the host from the kinetic energy before and after every kick: no speculation
+            for (uint64_t k = 0; k < steps; ++k) HXM_TRY(mdstep());
+            stat_launches += hx_launch_count() - launches0;
+            return 0;
+        }
 
         HXM_TRY(f->ensure(false));                 // forces for the current positions (first step only)
         bool pending_finalize = false;             // velocities still lack the second half-kick of the last step
@@ -1099,7 +1173,41 @@ int hxm_integrator_set_temperature(hxm_integrator* i, double temperature)
 {
     if (!i || !(temperature >= 0)) return HX_E_INVALID;
     i->temperature = temperature;
-    i->update_andersen();
+    if (i->kind == hxm_integrator::HOOVER) i->update_hoover();
+    else i->update_andersen();
+    return 0;
+}
+
+int hxm_integrator_hoover_create(hxm_particle* particle, hxm_force* force, const double box_length[3], double timestep,
+                                 double temperature, double resonance_frequency, hxm_integrator** out)
+{
+    if (!(temperature > 0) || !(resonance_frequency > 0)) { set_error("integrators.verlet_nvt_hoover: invalid argument"); return HX_E_INVALID; }
+    hxm_integrator* i = nullptr;
+    HXM_TRY(integrator_create(hxm_integrator::HOOVER, particle, force, box_length, timestep, &i));
+    std::unique_ptr<hxm_integrator> guard(i);
+    i->temperature = temperature;
+    i->resonance_frequency = resonance_frequency;
+    i->update_hoover();
+    HXM_TRY(dev_alloc(&i->d_hoover, 8));
+    HXM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&i->h_hoover), 8 * sizeof(double)));
+    *out = guard.release();
+    return 0;
+}
+
+int hxm_integrator_hoover_set_mass(hxm_integrator* i, const double mass[2])
+{
+    if (!i || !mass || i->kind != hxm_integrator::HOOVER || !(mass[0] > 0) || !(mass[1] > 0)) return HX_E_INVALID;
+    i->mass_xi[0] = mass[0];
+    i->mass_xi[1] = mass[1];
+    return 0;
+}
+
+/* out = (xi[0], xi[1], v_xi[0], v_xi[1], mass_xi[0], mass_xi[1], en_nhc per particle) */
+int hxm_integrator_hoover_state(const hxm_integrator* i, double out[7])
+{
+    if (!i || !out || i->kind != hxm_integrator::HOOVER) return HX_E_INVALID;
+    out[0] = i->xi[0]; out[1] = i->xi[1]; out[2] = i->v_xi[0]; out[3] = i->v_xi[1];
+    out[4] = i->mass_xi[0]; out[5] = i->mass_xi[1]; out[6] = i->en_nhc;
     return 0;
 }
 

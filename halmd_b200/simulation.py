@@ -78,7 +78,7 @@ class System:
 
 def lennard_jones_fluid(n, density=0.8442, temperature=1.2, cutoff=2.5, truncation="smooth_r4", h=0.005, timestep=0.001,
                         skin=0.5, seed=1, layout="row", occupancy=None, integrator="verlet", rate=2.0,
-                        disable_sorting=False, shuffle=True):
+                        disable_sorting=False, shuffle=True, resonance_frequency=5.0, start_temperature=None):
     """BASELINE configs 1/2: one-component LJ fluid on an fcc lattice with Maxwell-Boltzmann velocities."""
     L = (n / density) ** (1.0 / 3)
     rng = np.random.default_rng(seed)
@@ -88,7 +88,7 @@ def lennard_jones_fluid(n, density=0.8442, temperature=1.2, cutoff=2.5, truncati
     if shuffle:
         pos = pos[rng.permutation(n)]          # particle order carries no spatial information initially
     particle.set("position", pos.astype(np.float32))
-    particle.set("velocity_ds", boltzmann_velocities(n, temperature, rng))
+    particle.set("velocity_ds", boltzmann_velocities(n, temperature if start_temperature is None else start_temperature, rng))
     potential = mdsim.potentials.pair.lennard_jones()
     potential = potential.truncate(truncation, cutoff=cutoff, h=h) if truncation == "smooth_r4" else \
         potential.truncate(truncation, cutoff=cutoff)
@@ -97,6 +97,9 @@ def lennard_jones_fluid(n, density=0.8442, temperature=1.2, cutoff=2.5, truncati
     force = mdsim.forces.pair(box=box, particle=particle, potential=potential, neighbour=nb)
     if integrator == "verlet":
         integ = mdsim.integrators.verlet(box=box, particle=particle, timestep=timestep)
+    elif integrator == "hoover":
+        integ = mdsim.integrators.verlet_nvt_hoover(box=box, particle=particle, timestep=timestep,
+                                                    temperature=temperature, resonance_frequency=resonance_frequency)
     else:
         integ = mdsim.integrators.verlet_nvt_andersen(box=box, particle=particle, timestep=timestep,
                                                       temperature=temperature, rate=rate, seed=seed)

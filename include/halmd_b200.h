@@ -226,6 +226,15 @@ int hx_verlet_finalize_integrate(hx_float4* position_dev, hx_float4* image_dev,
 int hx_verlet_finalize_guarded(hx_float4* velocity_dev, const hx_float4* force_dev,
                                size_t array_size, float timestep, uint32_t* ctl_dev, void* stream);
 
+/* ---- f3: Nose-Hoover chain thermostat (halmd/mdsim/gpu/integrators/verlet_nvt_hoover_kernel.cu:37-125) ------------
+ * integrate: v *= scale (double-single), then the first velocity-Verlet half-step; rescale: v *= scale.  The second
+ * half-step is hx_verlet_finalize.  `scale` is the factor returned by the host-side chain propagation
+ * (verlet_nvt_hoover.cpp:185-222), converted to double-single like halmd::dsfloat(double). */
+int hx_hoover_integrate(hx_float4* position_dev, hx_float4* image_dev, hx_float4* velocity_dev,
+                        const hx_float4* force_dev, size_t array_size, float timestep, double scale,
+                        const float box_length[3], void* stream);
+int hx_hoover_rescale(hx_float4* velocity_dev, size_t array_size, double scale, void* stream);
+
 /* ---- a13: Andersen thermostat with rand48 ---------------------------------------------------
  * halmd/random/gpu/rand48.hpp:57-81, rand48_kernel.cu:42-100, rand48_kernel.cuh:40-79,
  * halmd/mdsim/gpu/integrators/verlet_nvt_andersen_kernel.cu:96-171. */

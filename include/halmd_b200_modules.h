@@ -117,6 +117,13 @@ int hxm_integrator_verlet_create(hxm_particle* particle, hxm_force* force, const
 int hxm_integrator_andersen_create(hxm_particle* particle, hxm_force* force, const double box_length[3],
                                    double timestep, double temperature, double rate, unsigned seed,
                                    hxm_integrator** out);
+/* mdsim.integrators.verlet_nvt_hoover{box, particle, timestep, temperature, resonance_frequency}
+ * (halmd/mdsim/gpu/integrators/verlet_nvt_hoover.cpp:40-222): Nose-Hoover chain of length 2; the chain is propagated on
+ * the host twice per step.  hoover_state: (xi[0], xi[1], v_xi[0], v_xi[1], mass_xi[0], mass_xi[1], en_nhc per particle). */
+int hxm_integrator_hoover_create(hxm_particle* particle, hxm_force* force, const double box_length[3], double timestep,
+                                 double temperature, double resonance_frequency, hxm_integrator** out);
+int hxm_integrator_hoover_state(const hxm_integrator* i, double out[7]);
+int hxm_integrator_hoover_set_mass(hxm_integrator* i, const double mass[2]);
 void hxm_integrator_destroy(hxm_integrator* i);
 int hxm_integrator_integrate(hxm_integrator* i);
 int hxm_integrator_finalize(hxm_integrator* i);

@@ -14,6 +14,7 @@
 #include <halmd/mdsim/gpu/potentials/external/planar_wall_kernel.hpp>
 #include <halmd/mdsim/gpu/integrators/verlet_kernel.hpp>
 #include <halmd/mdsim/gpu/integrators/verlet_nvt_andersen_kernel.hpp>
+#include <halmd/mdsim/gpu/integrators/verlet_nvt_hoover_kernel.hpp>
 #include <halmd/random/gpu/rand48_kernel.cuh>
 #include <halmd/mdsim/gpu/max_displacement_kernel.hpp>
 #include <halmd/mdsim/gpu/neighbours/from_binning_kernel.hpp>
@@ -274,6 +275,42 @@ int refgpu_verlet(int do_finalize, int do_integrate, float* position8, float* im
         if (do_integrate) {
             wrapper_type::wrapper.integrate.configure(grid, block);
             wrapper_type::wrapper.integrate(pos, d_img.p, vel, d_f.p, timestep, vec3<fixed_vector<float, 3>>(box_length));
+        }
+    )
+    RG_CHECK(cudaDeviceSynchronize());
+    int rc;
+    if ((rc = d_pos.down(reinterpret_cast<float4*>(position8)))) return rc;
+    if ((rc = d_vel.down(reinterpret_cast<float4*>(velocity8)))) return rc;
+    return d_img.down(reinterpret_cast<float4*>(image4));
+}
+
+// integrators::verlet_nvt_hoover (verlet_nvt_hoover.cpp:103-183): which = 0 integrate(scale), 1 finalize, 2 rescale(scale);
+// the host passes its double-precision scale factor through dsfloat's converting constructor
+int refgpu_hoover(int which, float* position8, float* image4, float* velocity8, const float* force4, size_t array_size,
+                  float timestep, double scale, const float box_length[3])
+{
+    typedef integrators::verlet_nvt_hoover_wrapper<3, dsfloat> wrapper_type;
+    typedef wrapper_type::ptr_type ptr_type;
+    if (array_size % 128 != 0) return static_cast<int>(cudaErrorInvalidValue);
+    dbuf<float4> d_pos(reinterpret_cast<const float4*>(position8), 2 * array_size);
+    dbuf<float4> d_vel(reinterpret_cast<const float4*>(velocity8), 2 * array_size);
+    dbuf<float4> d_img(reinterpret_cast<const float4*>(image4), array_size);
+    dbuf<float4> d_f(reinterpret_cast<const float4*>(force4), array_size);
+    if (!d_pos.p || !d_vel.p || !d_img.p || !d_f.p) return static_cast<int>(cudaErrorMemoryAllocation);
+    ptr_type pos = {d_pos.p, d_pos.p + array_size}, vel = {d_vel.p, d_vel.p + array_size};
+    dim3 const grid(static_cast<unsigned>(array_size / 128)), block(128);
+    RG_TRY(
+        if (which == 0) {
+            wrapper_type::kernel.integrate.configure(grid, block);
+            wrapper_type::kernel.integrate(pos, d_img.p, vel, d_f.p, timestep, dsfloat(scale), vec3<fixed_vector<float, 3>>(box_length));
+        }
+        else if (which == 1) {
+            wrapper_type::kernel.finalize.configure(grid, block);
+            wrapper_type::kernel.finalize(vel, d_f.p, timestep);
+        }
+        else {
+            wrapper_type::kernel.rescale.configure(grid, block);
+            wrapper_type::kernel.rescale(vel, dsfloat(scale));
         }
     )
     RG_CHECK(cudaDeviceSynchronize());

@@ -220,6 +220,46 @@ def test_andersen_thermostat_reaches_temperature(api):
     assert abs(np.mean(temps) - 1.5) < 0.03
 
 
+def test_hoover_thermostat(api):
+    """test/unit/mdsim/integrators/verlet_nvt_hoover.cpp:134-262 with a shorter run: N = 1500 WCA particles at
+    rho = 0.1, T 3 -> 1, f_res = 5, dt = 0.002.  The Hamiltonian extended by the chain terms is conserved (the
+    reference's GPU gate max(6e-5 here 1e-4 for the mixed accumulators, steps * 1e-12)), the centre of mass stays at
+    rest, mean temperature and its fluctuations (kinetic specific heat 3/2) follow the canonical ensemble."""
+    _, simulation = api
+    n, temp, dt, fres = 1500, 1.0, 0.002, 5.0
+    s = simulation.lennard_jones_fluid(n, density=0.1, temperature=temp, start_temperature=3.0, cutoff=2 ** (1 / 6),
+                                       truncation="shifted", timestep=dt, skin=0.5, seed=21, integrator="hoover",
+                                       resonance_frequency=fres)
+    assert s.integrator.mass == pytest.approx([3 * n * temp / (2 * np.pi * fres) ** 2, temp / (2 * np.pi * fres) ** 2])
+    steps = int(np.ceil(100 / dt))
+    skip = int(np.ceil(20 / dt))
+    period = int(round(3 / (fres * dt)))
+    s.run(steps // 20)
+    th = s.thermodynamics()
+    h0 = th["internal_energy"] + s.integrator.internal_energy
+    temps, vcm, worst = [], [], 0.0
+    for i in range(0, steps, period):
+        s.run(period)
+        th = s.thermodynamics()
+        if i >= skip:
+            temps.append(th["temperature"])
+        vcm.append(th["center_of_mass_velocity"])
+        worst = max(worst, abs(th["internal_energy"] + s.integrator.internal_energy - h0))
+    assert worst / abs(h0) < 1e-4, (worst, h0)
+    assert np.abs(np.mean(vcm, axis=0)).max() < 1e-5
+    c = len(temps)
+    assert abs(np.mean(temps) / temp - 1) < 4.5 * np.sqrt(2.0 / (3 * n * (c - 1))) / temp
+    cv = 1.5 ** 2 * n * np.var(temps, ddof=1)
+    assert abs(cv / 1.5 - 1) < 4.5 * np.sqrt(1.5 * (3 + 6.0 / n) / c) / 1.5
+    xi, v_xi = s.integrator.position, s.integrator.velocity
+    assert len(xi) == 2 and len(v_xi) == 2 and xi[0] != 0
+    # set_temperature rescales the chain masses (verlet_nvt_hoover.cpp:79-95); set_mass overrides them
+    s.integrator.set_temperature(2.0)
+    assert s.integrator.mass[1] == pytest.approx(2.0 / (2 * np.pi * fres) ** 2)
+    s.integrator.set_mass([3.0, 0.5])
+    assert s.integrator.mass == [3.0, 0.5]
+
+
 def test_kob_andersen_mixture(api):
     """BASELINE config 3 (scaled down): binary mixture with Andersen thermostat, then NVE energy conservation."""
     _, simulation = api
