@@ -32,6 +32,7 @@ struct nlist_args {
 constexpr unsigned NL_THREADS = 256;
 constexpr unsigned NL_WARPS = NL_THREADS / 32;
 constexpr unsigned NL_CELLS_PER_WARP = (27 + NL_WARPS - 1) / NL_WARPS;
+constexpr unsigned NL_PAD = 64;                // sentinel slots behind the staged particles
 constexpr unsigned NL_MAX_CHUNKS = 4;          // cell_size <= 128 keeps the staging loops fully unrolled
 
 __device__ __forceinline__ unsigned wrap_cell(int c, int d, int n)
@@ -67,49 +68,44 @@ __device__ __forceinline__ void nlist_lists(nlist_args const& a, const float4* s
     unsigned const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     unsigned const lane_lt = (1u << lane) - 1u;
     float const rr_cut0 = a.rr_cut_skin[0];
+    unsigned const Mpad = (M + 63u) & ~63u;          // [M, Mpad) holds NaN sentinels that fail every distance test
+    unsigned const size = a.size;
     for (unsigned p = warp; p < home_cnt; p += NL_WARPS) {
         unsigned const n = s_id[home_off + p];
         if (n >= a.nbuild) break;                  // ascending indices within a cell: the rest are partners only
         float4 const r1 = s_pos[home_off + p];
         unsigned* row = ROW ? a.g_neighbour + static_cast<size_t>(n) * a.stride : a.g_neighbour + n;
+        if (ROW) asm volatile("" : "+l"(row));     // keep the row base in registers instead of recomputing it per store
+        const unsigned* si = s_id + lane;
+        const float4* sp = s_pos + lane;
         unsigned count = 0;
         // two chunks per trip: independent shared-memory loads and distance chains in flight
-        for (unsigned base = 0; base < M; base += 64) {
-            unsigned count2 = count;
-            // (the second chunk's slots follow the first's: evaluate both tests, then compact in order)
-            bool ok0 = false, ok1 = false;
-            unsigned m0 = HX_PH, m1 = HX_PH;
-            unsigned const e0 = base + lane, e1 = base + 32 + lane;
-            float4 q0, q1;
-            if (e0 < M) { m0 = s_id[e0]; q0 = s_pos[e0]; }
-            if (e1 < M) { m1 = s_id[e1]; q1 = s_pos[e1]; }
-            if (e0 < M) {
-                float dx = __fsub_rn(r1.x, q0.x), dy = __fsub_rn(r1.y, q0.y), dz = __fsub_rn(r1.z, q0.z);
-                if (IMG) { dx = minimg(dx, a.L.x, a.invL.x); dy = minimg(dy, a.L.y, a.invL.y); dz = minimg(dz, a.L.z, a.invL.z); }
-                float const cut = TYPED ? s_rr[__float_as_uint(r1.w) * a.ntype2 + __float_as_uint(q0.w)] : rr_cut0;
-                ok0 = (m0 != n) && (norm2(dx, dy, dz) <= cut);          // note <= : from_binning_kernel.cu:143
+        for (unsigned base = 0; base < Mpad; base += 64) {
+            unsigned const m0 = si[base], m1 = si[base + 32];
+            float4 const q0 = sp[base], q1 = sp[base + 32];
+            float dx0 = __fsub_rn(r1.x, q0.x), dy0 = __fsub_rn(r1.y, q0.y), dz0 = __fsub_rn(r1.z, q0.z);
+            float dx1 = __fsub_rn(r1.x, q1.x), dy1 = __fsub_rn(r1.y, q1.y), dz1 = __fsub_rn(r1.z, q1.z);
+            if (IMG) {
+                dx0 = minimg(dx0, a.L.x, a.invL.x); dy0 = minimg(dy0, a.L.y, a.invL.y); dz0 = minimg(dz0, a.L.z, a.invL.z);
+                dx1 = minimg(dx1, a.L.x, a.invL.x); dy1 = minimg(dy1, a.L.y, a.invL.y); dz1 = minimg(dz1, a.L.z, a.invL.z);
             }
-            if (e1 < M) {
-                float dx = __fsub_rn(r1.x, q1.x), dy = __fsub_rn(r1.y, q1.y), dz = __fsub_rn(r1.z, q1.z);
-                if (IMG) { dx = minimg(dx, a.L.x, a.invL.x); dy = minimg(dy, a.L.y, a.invL.y); dz = minimg(dz, a.L.z, a.invL.z); }
-                float const cut = TYPED ? s_rr[__float_as_uint(r1.w) * a.ntype2 + __float_as_uint(q1.w)] : rr_cut0;
-                ok1 = (m1 != n) && (norm2(dx, dy, dz) <= cut);
-            }
+            float const cut0 = TYPED ? s_rr[__float_as_uint(r1.w) * a.ntype2 + __float_as_uint(q0.w)] : rr_cut0;
+            float const cut1 = TYPED ? s_rr[__float_as_uint(r1.w) * a.ntype2 + __float_as_uint(q1.w)] : rr_cut0;
+            bool const ok0 = (m0 != n) && (norm2(dx0, dy0, dz0) <= cut0);          // note <= : from_binning_kernel.cu:143
+            bool const ok1 = (m1 != n) && (norm2(dx1, dy1, dz1) <= cut1);
             unsigned const mask0 = __ballot_sync(0xFFFFFFFFu, ok0);
             unsigned const mask1 = __ballot_sync(0xFFFFFFFFu, ok1);
-            unsigned const slot0 = count2 + __popc(mask0 & lane_lt);
-            count2 += __popc(mask0);
-            unsigned const slot1 = count2 + __popc(mask1 & lane_lt);
-            count2 += __popc(mask1);
-            if (ok0 && slot0 < a.size) {
-                if (ROW) row[slot0] = m0;
-                else row[static_cast<size_t>(slot0) * a.stride] = m0;
+            unsigned const slot0 = count + __popc(mask0 & lane_lt);
+            count += __popc(mask0);
+            unsigned const slot1 = count + __popc(mask1 & lane_lt);
+            count += __popc(mask1);
+            if (ROW) {
+                if (ok0 && slot0 < size) row[slot0] = m0;
+                if (ok1 && slot1 < size) row[slot1] = m1;
+            } else {
+                if (ok0 && slot0 < size) row[static_cast<size_t>(slot0) * a.stride] = m0;
+                if (ok1 && slot1 < size) row[static_cast<size_t>(slot1) * a.stride] = m1;
             }
-            if (ok1 && slot1 < a.size) {
-                if (ROW) row[slot1] = m1;
-                else row[static_cast<size_t>(slot1) * a.stride] = m1;
-            }
-            count = count2;
         }
         if (count >= a.size) {
             // from_binning_kernel.cu:263-266 — list fully occupied ⇒ overcrowded
@@ -147,8 +143,8 @@ __global__ void __launch_bounds__(NL_THREADS) k_nlist_build(nlist_args a)
     int const cy = (cell / a.ncell.x) % a.ncell.y;
     int const cz = cell / a.ncell.x / a.ncell.y;
 
-    float4* s_pos = s_dyn;                                             // [27*cs] (x, y, z, species)
-    unsigned* s_id = reinterpret_cast<unsigned*>(s_dyn + 27 * cs);     // [27*cs]
+    float4* s_pos = s_dyn;                                             // [27*cs + NL_PAD] (x, y, z, species)
+    unsigned* s_id = reinterpret_cast<unsigned*>(s_dyn + 27 * cs + NL_PAD);     // [27*cs + NL_PAD]
     if (threadIdx.x < HX_MAX_PAIR_TYPES) s_rr[threadIdx.x] = a.rr_cut_skin[threadIdx.x];
 
     // phase 1: occupancy of the 27 cells; the loads of a warp's cells are independent and issued together
@@ -194,6 +190,13 @@ __global__ void __launch_bounds__(NL_THREADS) k_nlist_build(nlist_args a)
     __syncthreads();
     // phase 2: stage ids and positions, packed in visiting order; ids (L1/L2 hits now) and the dependent position
     // gathers of all of a warp's cells are in flight together.  Each lane tracks the extent of what it staged.
+    if (threadIdx.x < NL_PAD) {
+        // sentinels behind the staged entries: the list loop runs over whole pairs of chunks without bounds tests
+        unsigned const M = s_off[27];
+        float const qnan = __uint_as_float(0x7FC00000u);
+        s_id[M + threadIdx.x] = HX_PH;
+        s_pos[M + threadIdx.x] = make_float4(qnan, qnan, qnan, 0.f);
+    }
     float const big = 3.0e38f;
     float lo_x = big, lo_y = big, lo_z = big, hi_x = -big, hi_y = -big, hi_z = -big;
     auto stage = [&](unsigned slot, unsigned id) {
@@ -292,7 +295,7 @@ static int nlist_build_impl(const uint32_t* g_cell_dev, const unsigned ncell[3],
     }
     cudaStream_t st = as_stream(stream);
     size_t ncells = static_cast<size_t>(ncell[0]) * ncell[1] * ncell[2];
-    size_t smem = static_cast<size_t>(27) * cell_size * (sizeof(float4) + sizeof(unsigned));
+    size_t smem = (static_cast<size_t>(27) * cell_size + NL_PAD) * (sizeof(float4) + sizeof(unsigned));
     if (smem > 200 * 1024) {
         set_error("hx_nlist_build: cell size %u exceeds shared memory staging capacity", cell_size);
         return HX_E_UNSUPPORTED;
