@@ -30,6 +30,7 @@ class LjParams(C.Structure):
         ("epsilon", C.c_float * MAX_PAIR_TYPES), ("sigma2", C.c_float * MAX_PAIR_TYPES),
         ("r_cut", C.c_float * MAX_PAIR_TYPES), ("rr_cut", C.c_float * MAX_PAIR_TYPES),
         ("en_cut", C.c_float * MAX_PAIR_TYPES), ("force_cut", C.c_float * MAX_PAIR_TYPES),
+        ("hard_core", C.c_int), ("r_core", C.c_float * MAX_PAIR_TYPES),
     ]
 
 
@@ -86,6 +87,7 @@ _protos = {
     "hx_nlist_build": (C.c_int, [P, U3, C.c_uint, P, SZ, F3, C.c_uint, C.c_uint, F3, P, C.c_uint, SZ,
                                  C.c_int, C.c_int, P, P, P]),
     "hx_potential_lj_init": (C.c_int, [C.POINTER(LjParams), C.c_uint, C.c_uint, F3, F3, C.c_int, F3, C.c_float]),
+    "hx_potential_lj_init_hard_core": (C.c_int, [C.POINTER(LjParams), C.c_uint, C.c_uint, F3, F3, F3, C.c_int, F3, C.c_float]),
     "hx_pair_force": (C.c_int, [C.POINTER(LjParams), P, P, P, C.c_uint, SZ, C.c_int, SZ, F3, C.c_int,
                                 C.c_float, P, P, P, SZ, P]),
     "hx_planar_wall_init": (C.c_int, [C.POINTER(PlanarWall), C.c_uint, C.c_uint, F3, F3, F3, F3, F3, F3, C.c_float]),
@@ -142,6 +144,7 @@ _module_protos = {
     "hxm_particle_device_ptr": (P, [P, C.c_char_p]),
     "hxm_particle_aux_enable": (C.c_int, [P]),
     "hxm_potential_lj_create": (C.c_int, [C.c_uint, C.c_uint, F3, F3, C.c_int, F3, C.c_float, PP]),
+    "hxm_potential_lj_hard_core_create": (C.c_int, [C.c_uint, C.c_uint, F3, F3, F3, C.c_int, F3, C.c_float, PP]),
     "hxm_potential_destroy": (None, [P]),
     "hxm_potential_r_cut": (C.c_int, [P, F3]),
     "hxm_potential_params": (C.POINTER(LjParams), [P]),

@@ -144,6 +144,21 @@ class _lennard_jones:
         self.species = int(n)
         self.epsilon = _matrix(epsilon, n, n, "epsilon")
         self.sigma = _matrix(sigma, n, n, "sigma")
+        self.r_core_sigma = None
+
+    def modify(self, *args, **kw):
+        """potential:modify({"hard_core", radius = ...}) (adapters/modify.lua.in): the potential is evaluated at
+        r - radius * sigma.  Returns a new potential that can be truncated."""
+        spec = dict(args[0]) if args and isinstance(args[0], dict) else dict(kw)
+        kind = spec.pop("type", None) or (args[0] if args and isinstance(args[0], str) else None)
+        if kind != "hard_core":
+            raise ValueError(f"invalid modification type '{kind}'")
+        if "radius" not in spec and "radius" not in kw:
+            raise ValueError("missing argument 'radius'")
+        radius = spec.get("radius", kw.get("radius"))
+        new = _lennard_jones(self.epsilon, self.sigma, self.species)
+        new.r_core_sigma = _matrix(radius, self.species, self.species, "radius")
+        return new
 
     def truncate(self, type=None, cutoff=None, h=None, **kw):
         """potential:truncate{[type], cutoff=..., h=...}; the default truncation is 'shifted' (truncate.lua.in:289)."""
@@ -172,8 +187,14 @@ class _truncated(_Handle):
         self.species = parent.species
         self.epsilon, self.sigma = parent.epsilon, parent.sigma
         n = parent.species
-        check(lib.hxm_potential_lj_create(n, n, hx.farr(parent.epsilon.ravel()), hx.farr(parent.sigma.ravel()), trunc,
-                                          hx.farr(cutoff.ravel()), h, C.byref(self._h)), "potential")
+        self.r_core_sigma = parent.r_core_sigma
+        if parent.r_core_sigma is not None:
+            check(lib.hxm_potential_lj_hard_core_create(n, n, hx.farr(parent.epsilon.ravel()), hx.farr(parent.sigma.ravel()),
+                                                        hx.farr(parent.r_core_sigma.ravel()), trunc,
+                                                        hx.farr(cutoff.ravel()), h, C.byref(self._h)), "potential")
+        else:
+            check(lib.hxm_potential_lj_create(n, n, hx.farr(parent.epsilon.ravel()), hx.farr(parent.sigma.ravel()), trunc,
+                                              hx.farr(cutoff.ravel()), h, C.byref(self._h)), "potential")
         out = (C.c_float * (n * n))()
         check(lib.hxm_potential_r_cut(self._h, out))
         self.r_cut = np.array(list(out), dtype=np.float32).reshape(n, n)

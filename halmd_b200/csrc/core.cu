@@ -128,6 +128,13 @@ int hx_displacement_exceeds(uint32_t max_rr_bits, double skin)
 int hx_potential_lj_init(hx_lj_params* p, unsigned ntype1, unsigned ntype2, const float* epsilon,
                          const float* sigma, int truncation, const float* cutoff_sigma, float h)
 {
+    return hx_potential_lj_init_hard_core(p, ntype1, ntype2, epsilon, sigma, nullptr, truncation, cutoff_sigma, h);
+}
+
+int hx_potential_lj_init_hard_core(hx_lj_params* p, unsigned ntype1, unsigned ntype2, const float* epsilon,
+                                   const float* sigma, const float* core_sigma, int truncation,
+                                   const float* cutoff_sigma, float h)
+{
     if (!p || !epsilon || !sigma || !cutoff_sigma || ntype1 == 0 || ntype2 == 0
         || ntype1 * ntype2 > HX_MAX_PAIR_TYPES) {
         set_error("hx_potential_lj_init: invalid argument (ntype1*ntype2 must be in 1..%d)", HX_MAX_PAIR_TYPES);
@@ -141,6 +148,7 @@ int hx_potential_lj_init(hx_lj_params* p, unsigned ntype1, unsigned ntype2, cons
     p->ntype1 = ntype1;
     p->ntype2 = ntype2;
     p->truncation = truncation;
+    p->hard_core = core_sigma != nullptr;
     // rri_smooth_(std::pow(h, -2)): pow(float, int) is evaluated in double, stored as float
     p->rri_smooth = (truncation == HX_TRUNC_SMOOTH_R4)
         ? static_cast<float>(std::pow(static_cast<double>(h), -2)) : 0.f;
@@ -149,12 +157,22 @@ int hx_potential_lj_init(hx_lj_params* p, unsigned ntype1, unsigned ntype2, cons
         float sigma2 = sigma[i] * sigma[i];
         float r_cut = sigma[i] * cutoff_sigma[i];
         float rr_cut = r_cut * r_cut;
-        // host-side operator() of the float potential, evaluated at rr_cut
-        float rri = sigma2 / rr_cut;
+        // host-side operator() of the float potential, evaluated at rr_cut; through the hard-core adapter
+        // (adapters/hard_core.hpp:86-94) at (sqrt(rr_cut) - r_core)^2, the force scaled by r_s / r
+        float r_core = core_sigma ? core_sigma[i] * sigma[i] : 0.f;
+        if (core_sigma && !(r_core >= 0.f && r_core < r_cut)) {
+            set_error("hx_potential_lj_init_hard_core: core radius must lie in [0, r_cut)");
+            return HX_E_INVALID;
+        }
+        float r = std::sqrt(rr_cut);
+        float r_s = r - r_core;
+        float rri = sigma2 / (core_sigma ? r_s * r_s : rr_cut);
         float r6i = rri * rri * rri;
         float eps_r6i = eps * r6i;
         float en_cut = 4 * eps_r6i * (r6i - 1);
         float fval_cut = 48 * rri * eps_r6i * (r6i - 0.5f) / sigma2;
+        if (core_sigma) fval_cut *= r_s / r;
+        p->r_core[i] = r_core;
         p->epsilon[i] = eps;
         p->sigma2[i] = sigma2;
         p->r_cut[i] = r_cut;

@@ -926,6 +926,17 @@ int hxm_potential_lj_create(unsigned ntype1, unsigned ntype2, const float* epsil
     return 0;
 }
 
+int hxm_potential_lj_hard_core_create(unsigned ntype1, unsigned ntype2, const float* epsilon, const float* sigma,
+                                      const float* core_sigma, int truncation, const float* cutoff_sigma, float h,
+                                      hxm_potential** out)
+{
+    if (!out || !core_sigma) return HX_E_INVALID;
+    auto p = std::unique_ptr<hxm_potential>(new hxm_potential);
+    HXM_TRY(hx_potential_lj_init_hard_core(&p->p, ntype1, ntype2, epsilon, sigma, core_sigma, truncation, cutoff_sigma, h));
+    *out = p.release();
+    return 0;
+}
+
 void hxm_potential_destroy(hxm_potential* p) { delete p; }
 
 int hxm_potential_r_cut(const hxm_potential* p, float* r_cut_out)

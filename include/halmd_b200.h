@@ -158,10 +158,18 @@ typedef struct hx_lj_params {
     float rr_cut[HX_MAX_PAIR_TYPES];
     float en_cut[HX_MAX_PAIR_TYPES];  /* U(r_cut), 0 for sharp */
     float force_cut[HX_MAX_PAIR_TYPES]; /* |F(r_cut)| = fval(r_cut) * r_cut (force_shifted.hpp:69-70), else 0 */
+    int hard_core;             /* adapters::hard_core<lennard_jones> (adapters/hard_core.hpp:46-100) */
+    float r_core[HX_MAX_PAIR_TYPES];  /* core * sigma; U(r) = U_LJ(r - r_core) */
 } hx_lj_params;
 
 int hx_potential_lj_init(hx_lj_params* p, unsigned ntype1, unsigned ntype2, const float* epsilon,
                          const float* sigma, int truncation, const float* cutoff_sigma, float h);
+/* potential:modify({"hard_core", radius = core_sigma}) before truncate (lennard_jones.lua.in:120-130):
+ * core_sigma[ntype1 * ntype2] in units of sigma (NULL: plain potential); en_cut / force_cut are those of the
+ * adapted potential at r_cut (shifted.hpp / force_shifted.hpp evaluate potential_type::operator()). */
+int hx_potential_lj_init_hard_core(hx_lj_params* p, unsigned ntype1, unsigned ntype2, const float* epsilon,
+                                   const float* sigma, const float* core_sigma, int truncation,
+                                   const float* cutoff_sigma, float h);
 
 /* ---- a8: truncated pair force ------------------------------------------------------------
  * halmd/mdsim/gpu/forces/pair_trunc.hpp:193-337, pair_trunc_kernel.cuh:54-255.

@@ -65,6 +65,10 @@ int hxm_particle_aux_enable(hxm_particle* p);
 /* ---- potential ------------------------------------------------------------------------------------------------ */
 int hxm_potential_lj_create(unsigned ntype1, unsigned ntype2, const float* epsilon, const float* sigma,
                             int truncation, const float* cutoff_sigma, float h, hxm_potential** out);
+/* potential:modify({"hard_core", radius = core_sigma}):truncate{...} (adapters/modify.lua.in, adapters/hard_core.hpp) */
+int hxm_potential_lj_hard_core_create(unsigned ntype1, unsigned ntype2, const float* epsilon, const float* sigma,
+                                      const float* core_sigma, int truncation, const float* cutoff_sigma, float h,
+                                      hxm_potential** out);
 void hxm_potential_destroy(hxm_potential* p);
 /* r_cut matrix (cutoff * sigma), row-major ntype1 x ntype2 */
 int hxm_potential_r_cut(const hxm_potential* p, float* r_cut_out);

@@ -350,6 +350,8 @@ typedef struct {
     int truncation;            /* 0 sharp, 1 shifted, 2 smooth_r4, 3 force_shifted */
     float rri_smooth;
     float epsilon[MAXPT], sigma2[MAXPT], r_cut[MAXPT], rr_cut[MAXPT], en_cut[MAXPT], force_cut[MAXPT];
+    int hard_core;             /* adapters/hard_core_kernel.hpp:37-84 */
+    float r_core[MAXPT];
 } lj_params;
 
 /* lennard_jones_kernel.hpp:43-56 */
@@ -362,8 +364,26 @@ static inline void lj_f(float rr, float sigma2, float eps, float* fval, float* e
     *en = 4 * eps_ri6 * (ri6 - 1);
 }
 
+/* adapters/hard_core_kernel.hpp:66-76 (device) = adapters/hard_core.hpp:86-94 (host, float) */
+static inline void lj_core_f(float rr, float r_core, float sigma2, float eps, float* fval, float* en)
+{
+    float r = sqrtf(rr);
+    float r_s = r - r_core;
+    lj_f(r_s * r_s, sigma2, eps, fval, en);
+    *fval *= r_s / r;
+}
+
+void oracle_lj_init_hard_core(lj_params* p, unsigned nt1, unsigned nt2, const float* eps, const float* sigma,
+                              const float* core_sigma, int trunc, const float* cutoff_sigma, float h);
+
 void oracle_lj_init(lj_params* p, unsigned nt1, unsigned nt2, const float* eps, const float* sigma, int trunc,
                     const float* cutoff_sigma, float h)
+{
+    oracle_lj_init_hard_core(p, nt1, nt2, eps, sigma, NULL, trunc, cutoff_sigma, h);
+}
+
+void oracle_lj_init_hard_core(lj_params* p, unsigned nt1, unsigned nt2, const float* eps, const float* sigma,
+                              const float* core_sigma, int trunc, const float* cutoff_sigma, float h)
 {
     /* lennard_jones.cpp:52-70, smooth_r4.hpp:55-91 */
     memset(p, 0, sizeof(*p));
@@ -371,13 +391,19 @@ void oracle_lj_init(lj_params* p, unsigned nt1, unsigned nt2, const float* eps, 
     p->ntype2 = nt2;
     p->truncation = trunc;
     p->rri_smooth = trunc == 2 ? (float)pow((double)h, -2) : 0.f;
+    p->hard_core = core_sigma != NULL;
     for (unsigned i = 0; i < nt1 * nt2; ++i) {
         p->epsilon[i] = eps[i];
         p->sigma2[i] = sigma[i] * sigma[i];
         p->r_cut[i] = sigma[i] * cutoff_sigma[i];
         p->rr_cut[i] = p->r_cut[i] * p->r_cut[i];
         float f, e;
-        lj_f(p->rr_cut[i], p->sigma2[i], p->epsilon[i], &f, &e);
+        if (core_sigma) {
+            p->r_core[i] = core_sigma[i] * sigma[i];       /* element_prod(core, sigma), adapters/hard_core.hpp:60 */
+            lj_core_f(p->rr_cut[i], p->r_core[i], p->sigma2[i], p->epsilon[i], &f, &e);
+        } else {
+            lj_f(p->rr_cut[i], p->sigma2[i], p->epsilon[i], &f, &e);
+        }
         p->en_cut[i] = trunc == 0 ? 0.f : e;
         p->force_cut[i] = trunc == 3 ? f * p->r_cut[i] : 0.f;      /* force_shifted.hpp:69-70 */
     }
@@ -387,7 +413,8 @@ void oracle_lj_init(lj_params* p, unsigned nt1, unsigned nt2, const float* eps, 
 int oracle_pair_f(const lj_params* p, unsigned idx, float rr, float* fval, float* en)
 {
     if (!(rr < p->rr_cut[idx])) return 0;
-    lj_f(rr, p->sigma2[idx], p->epsilon[idx], fval, en);
+    if (p->hard_core) lj_core_f(rr, p->r_core[idx], p->sigma2[idx], p->epsilon[idx], fval, en);
+    else lj_f(rr, p->sigma2[idx], p->epsilon[idx], fval, en);
     if (p->truncation == 1) {
         *en = *en - p->en_cut[idx];                    /* shifted_kernel.cuh:49-57 */
     } else if (p->truncation == 2) {

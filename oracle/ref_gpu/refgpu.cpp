@@ -19,6 +19,7 @@
 #include <halmd/mdsim/gpu/max_displacement_kernel.hpp>
 #include <halmd/mdsim/gpu/neighbours/from_binning_kernel.hpp>
 #include <halmd/mdsim/gpu/particle_kernel.hpp>
+#include <halmd/mdsim/gpu/potentials/pair/adapters/hard_core_kernel.hpp>
 #include <halmd/mdsim/gpu/potentials/pair/lennard_jones_kernel.hpp>
 #include <halmd/mdsim/gpu/potentials/pair/truncations/force_shifted_kernel.hpp>
 #include <halmd/mdsim/gpu/potentials/pair/truncations/sharp_kernel.hpp>
@@ -36,6 +37,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <type_traits>
 #include <vector>
 
 using namespace halmd;
@@ -361,18 +363,17 @@ int launch_force(potential_type const& pot, const float4* pos, cudaTextureObject
 // truncations/{sharp,shifted,smooth_r4}.hpp upload them: (epsilon, sigma2); rr_cut; (rr_cut, en_cut);
 // (r_cut, rr_cut, en_cut); rri_smooth = h^-2 (smooth_r4.hpp:97).
 // force (in/out, array_size float4); en_pot (array_size) and stress (6 * array_size) may both be NULL (no aux).
-extern "C" int refgpu_pair_force(int truncation, unsigned ntype, const float* epsilon, const float* sigma2, const float* r_cut,
-                                 const float* rr_cut, const float* en_cut, const float* force_cut, float rri_smooth,
-                                 const float* position4,
-                                 size_t array_size, const uint32_t* g_neighbour, unsigned size, size_t stride, int layout,
-                                 const float box_length[3], int force_zero, float aux_weight, float* force4, float* en_pot,
-                                 float* stress)
+static int pair_force_impl(int truncation, unsigned ntype, const float* epsilon, const float* sigma2, const float* r_cut,
+                           const float* rr_cut, const float* en_cut, const float* force_cut, const float* r_core,
+                           float rri_smooth, const float* position4, size_t array_size, const uint32_t* g_neighbour,
+                           unsigned size, size_t stride, int layout, const float box_length[3], int force_zero,
+                           float aux_weight, float* force4, float* en_pot, float* stress)
 {
     if (array_size % 256 != 0) return static_cast<int>(cudaErrorInvalidValue);
     unsigned const np = ntype * ntype;
     std::vector<float2> h_lj(np), h_sh(np);
     std::vector<float4> h_sm(np), h_fs(np);
-    std::vector<float> h_sp(np);
+    std::vector<float> h_sp(np), h_core(np);
     for (unsigned t = 0; t < np; ++t) {
         h_lj[t] = make_float2(epsilon[t], sigma2[t]);                 // lennard_jones_kernel::EPSILON, SIGMA2
         h_sm[t] = make_float4(r_cut[t], rr_cut[t], en_cut[t], 0.f);   // smooth_r4_kernel::R_CUT, RR_CUT, EN_CUT
@@ -380,10 +381,11 @@ extern "C" int refgpu_pair_force(int truncation, unsigned ntype, const float* ep
         h_sp[t] = rr_cut[t];
         // force_shifted_kernel::R_CUT, RR_CUT, EN_CUT, FORCE_CUT
         h_fs[t] = make_float4(r_cut[t], rr_cut[t], en_cut[t], force_cut ? force_cut[t] : 0.f);
+        h_core[t] = r_core ? r_core[t] : 0.f;                         // adapters/hard_core.hpp:64-72
     }
     dbuf<float2> d_lj(h_lj.data(), np), d_sh(h_sh.data(), np);
     dbuf<float4> d_sm(h_sm.data(), np), d_fs(h_fs.data(), np);
-    dbuf<float> d_sp(h_sp.data(), np);
+    dbuf<float> d_sp(h_sp.data(), np), d_core(h_core.data(), np);
     size_t const nl_len = static_cast<size_t>(size) * stride;
     dbuf<float4> d_pos(reinterpret_cast<const float4*>(position4), array_size);
     dbuf<unsigned int> d_nl(g_neighbour, nl_len);
@@ -393,25 +395,34 @@ extern "C" int refgpu_pair_force(int truncation, unsigned ntype, const float* ep
     if (!d_pos.p || !d_nl.p || !d_f.p || !d_en.p || !d_st.p) return static_cast<int>(cudaErrorMemoryAllocation);
     lintex<float2> t_lj(d_lj.p, np), t_sh(d_sh.p, np);
     lintex<float4> t_sm(d_sm.p, np), t_fs(d_fs.p, np), t_r2(d_pos.p, array_size);
-    lintex<float> t_sp(d_sp.p, np);
-    lj::lennard_jones const parent(t_lj.t);
+    lintex<float> t_sp(d_sp.p, np), t_core(d_core.p, np);
     float* const en = aux ? d_en.p : nullptr;
     float* const st = aux ? d_st.p : nullptr;
     unsigned const pitch = static_cast<unsigned>(stride);
+    // truncation<parent>: the same four wrappers over the plain potential or its hard-core adapter
+    auto run = [&](auto const& parent) -> int {
+        typedef typename std::decay<decltype(parent)>::type parent_type;
+        if (truncation == 2) {
+            RG_TRY(tr::smooth_r4_wrapper<parent_type>::rri_smooth.set(rri_smooth))
+            tr::smooth_r4_kernel::smooth_r4<parent_type> pot(parent, t_sm.t);
+            return launch_force(pot, d_pos.p, t_r2.t, d_f.p, d_nl.p, size, pitch, layout, en, st, ntype, box_length, force_zero != 0, aux_weight, array_size);
+        } else if (truncation == 3) {
+            tr::force_shifted_kernel::force_shifted<parent_type> pot(parent, t_fs.t);
+            return launch_force(pot, d_pos.p, t_r2.t, d_f.p, d_nl.p, size, pitch, layout, en, st, ntype, box_length, force_zero != 0, aux_weight, array_size);
+        } else if (truncation == 1) {
+            tr::shifted_kernel::shifted<parent_type> pot(parent, t_sh.t);
+            return launch_force(pot, d_pos.p, t_r2.t, d_f.p, d_nl.p, size, pitch, layout, en, st, ntype, box_length, force_zero != 0, aux_weight, array_size);
+        }
+        tr::sharp_kernel::sharp<parent_type> pot(parent, t_sp.t);
+        return launch_force(pot, d_pos.p, t_r2.t, d_f.p, d_nl.p, size, pitch, layout, en, st, ntype, box_length, force_zero != 0, aux_weight, array_size);
+    };
+    lj::lennard_jones const plain(t_lj.t);
     int rc;
-    if (truncation == 2) {
-        RG_TRY(tr::smooth_r4_wrapper<lj::lennard_jones>::rri_smooth.set(rri_smooth))
-        tr::smooth_r4_kernel::smooth_r4<lj::lennard_jones> pot(parent, t_sm.t);
-        rc = launch_force(pot, d_pos.p, t_r2.t, d_f.p, d_nl.p, size, pitch, layout, en, st, ntype, box_length, force_zero != 0, aux_weight, array_size);
-    } else if (truncation == 3) {
-        tr::force_shifted_kernel::force_shifted<lj::lennard_jones> pot(parent, t_fs.t);
-        rc = launch_force(pot, d_pos.p, t_r2.t, d_f.p, d_nl.p, size, pitch, layout, en, st, ntype, box_length, force_zero != 0, aux_weight, array_size);
-    } else if (truncation == 1) {
-        tr::shifted_kernel::shifted<lj::lennard_jones> pot(parent, t_sh.t);
-        rc = launch_force(pot, d_pos.p, t_r2.t, d_f.p, d_nl.p, size, pitch, layout, en, st, ntype, box_length, force_zero != 0, aux_weight, array_size);
+    if (r_core) {
+        potentials::pair::adapters::hard_core_kernel::hard_core<lj::lennard_jones> const adapted(plain, t_core.t);
+        rc = run(adapted);
     } else {
-        tr::sharp_kernel::sharp<lj::lennard_jones> pot(parent, t_sp.t);
-        rc = launch_force(pot, d_pos.p, t_r2.t, d_f.p, d_nl.p, size, pitch, layout, en, st, ntype, box_length, force_zero != 0, aux_weight, array_size);
+        rc = run(plain);
     }
     if (rc) return rc;
     if ((rc = d_f.down(reinterpret_cast<float4*>(force4)))) return rc;
@@ -420,6 +431,32 @@ extern "C" int refgpu_pair_force(int truncation, unsigned ntype, const float* ep
         if ((rc = d_st.down(stress))) return rc;
     }
     return 0;
+}
+
+extern "C" int refgpu_pair_force(int truncation, unsigned ntype, const float* epsilon, const float* sigma2, const float* r_cut,
+                                 const float* rr_cut, const float* en_cut, const float* force_cut, float rri_smooth,
+                                 const float* position4,
+                                 size_t array_size, const uint32_t* g_neighbour, unsigned size, size_t stride, int layout,
+                                 const float box_length[3], int force_zero, float aux_weight, float* force4, float* en_pot,
+                                 float* stress)
+{
+    return pair_force_impl(truncation, ntype, epsilon, sigma2, r_cut, rr_cut, en_cut, force_cut, nullptr, rri_smooth, position4,
+                           array_size, g_neighbour, size, stride, layout, box_length, force_zero, aux_weight, force4, en_pot,
+                           stress);
+}
+
+// the same through adapters::hard_core<lennard_jones> (adapters/hard_core_kernel.hpp:37-84); r_core = core * sigma
+extern "C" int refgpu_pair_force_hard_core(int truncation, unsigned ntype, const float* epsilon, const float* sigma2,
+                                           const float* r_cut, const float* rr_cut, const float* en_cut,
+                                           const float* force_cut, const float* r_core, float rri_smooth,
+                                           const float* position4, size_t array_size, const uint32_t* g_neighbour,
+                                           unsigned size, size_t stride, int layout, const float box_length[3],
+                                           int force_zero, float aux_weight, float* force4, float* en_pot, float* stress)
+{
+    if (!r_core) return static_cast<int>(cudaErrorInvalidValue);
+    return pair_force_impl(truncation, ntype, epsilon, sigma2, r_cut, rr_cut, en_cut, force_cut, r_core, rri_smooth, position4,
+                           array_size, g_neighbour, size, stride, layout, box_length, force_zero, aux_weight, force4, en_pot,
+                           stress);
 }
 
 // forces::external<3, float, planar_wall> (external.hpp:120-190) with potentials::external::planar_wall

@@ -65,6 +65,7 @@ class OLjParams(C.Structure):
         ("ntype1", C.c_uint), ("ntype2", C.c_uint), ("truncation", C.c_int), ("rri_smooth", C.c_float),
         ("epsilon", C.c_float * MAXPT), ("sigma2", C.c_float * MAXPT), ("r_cut", C.c_float * MAXPT),
         ("rr_cut", C.c_float * MAXPT), ("en_cut", C.c_float * MAXPT), ("force_cut", C.c_float * MAXPT),
+        ("hard_core", C.c_int), ("r_core", C.c_float * MAXPT),
     ]
 
 

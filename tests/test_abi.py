@@ -64,6 +64,23 @@ def test_potential_tables_match_oracle(hx, oracle):
         assert bytes(p) == bytes(q)
 
 
+def test_hard_core_tables_match_oracle(hx, oracle):
+    """adapters/hard_core.hpp:56-72, :86-94 under the truncations: cutoff energy and force of the adapted potential."""
+    eps, sigma, cut, core = [1.0, 1.5, 1.5, 0.5], [1.0, 0.8, 0.8, 0.88], [2.5] * 4, [0.375, 0.5, 0.5, 0.0]
+    for trunc, h in ((0, 0.0), (1, 0.0), (2, 0.005), (3, 0.0)):
+        p = hx.LjParams()
+        hx.check(hx.lib.hx_potential_lj_init_hard_core(C.byref(p), 2, 2, hx.farr(eps), hx.farr(sigma), hx.farr(core), trunc,
+                                                       hx.farr(cut), h))
+        q = support.OLjParams()
+        oracle.oracle_lj_init_hard_core(C.byref(q), 2, 2, support.farr(eps), support.farr(sigma), support.farr(core), trunc,
+                                        support.farr(cut), C.c_float(h))
+        assert bytes(p) == bytes(q)
+        assert p.hard_core == 1 and list(p.r_core)[:4] == [np.float32(c) * np.float32(s) for c, s in zip(core, sigma)]
+    p = hx.LjParams()
+    assert hx.lib.hx_potential_lj_init_hard_core(C.byref(p), 1, 1, hx.farr([1.0]), hx.farr([1.0]), hx.farr([2.5]), 1,
+                                                 hx.farr([2.5]), 0.0) < 0       # core radius beyond the cutoff
+
+
 def test_planar_wall_tables_match_oracle(hx):
     """hx_planar_wall_init (host code in the product library) against the test-side restatement of
     planar_wall.cpp:83-112, with the parameters of the reference's unit test."""

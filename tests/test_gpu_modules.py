@@ -546,6 +546,52 @@ def test_ssf_of_fcc_lattice(api):
         assert abs(s[k, 0] - expect) < 2 * tol + 1e-3 * expect and s[k, 2] == hi - lo
 
 
+def test_hard_core_potential_through_modules(api):
+    """potential:modify({"hard_core", radius = 0.3}):truncate({"shifted", cutoff = 2^(1/6) + 0.3}) — soft spheres around
+    a core (lennard_jones.lua.in:120-130): forces equal those of plain WCA particles evaluated at r - r_core and scaled
+    by (r - r_core) / r (checked pair by pair on a dilute configuration), and an NVE run conserves energy."""
+    halmd_b200, simulation = api
+    from halmd_b200 import mdsim
+    n, rho = 4000, 0.3
+    L = (n / rho) ** (1 / 3)
+    rng = np.random.default_rng(31)
+    box = mdsim.box(length=[L, L, L])
+    particle = mdsim.particle(dimension=3, particles=n, species=1)
+    pos = simulation.fcc_positions(n, box.length).astype(np.float32)
+    particle.set("position", pos)
+    particle.set("velocity_ds", simulation.boltzmann_velocities(n, 1.0, rng))
+    core, cut = 0.3, 2 ** (1 / 6) + 0.3
+    pot = mdsim.potentials.pair.lennard_jones().modify("hard_core", radius=core)
+    pot = pot.truncate("shifted", cutoff=cut)
+    assert pot.params.hard_core == 1 and pot.params.r_core[0] == np.float32(core)
+    nb = mdsim.neighbour(particle=particle, box=box, r_cut=pot.r_cut, skin=0.5)
+    force = mdsim.forces.pair(box=box, particle=particle, potential=pot, neighbour=nb)
+    integ = mdsim.integrators.verlet(box=box, particle=particle, timestep=0.002)
+    core_ = mdsim.core.get()
+    core_.run(500)
+    th0 = core_.thermodynamics()
+    core_.run(5000)
+    th = core_.thermodynamics()
+    assert abs(th["internal_energy"] - th0["internal_energy"]) < 2e-4 * abs(th0["internal_energy"]) + 2e-5
+    assert th["potential_energy"] > 0          # purely repulsive, shifted to zero at the cutoff
+    # brute-force forces in double on the final configuration
+    r = particle.get("position").astype(np.float32)
+    f = particle.get("force").astype(np.float64)[:, :3]
+    sample = rng.choice(n, 200, replace=False)
+    Lf = np.float32(L)
+    for i in sample:
+        # separations as the kernels see them: single-precision difference and minimum image (a pair across the
+        # boundary carries the rounding of a difference of magnitude L), everything after that in double
+        d = r[i] - r
+        d = (d - np.rint(d / Lf) * Lf).astype(np.float64)
+        dist = np.sqrt((d ** 2).sum(axis=1))
+        m = (dist > 0) & (dist < cut)
+        rs = dist[m] - core
+        fv = 24 * (2 * rs ** -12 - rs ** -6) / rs / dist[m]
+        fi = (fv[:, None] * d[m]).sum(axis=0)
+        assert np.abs(fi - f[i]).max() < 2e-5 * max(1.0, np.abs(fi).max())
+
+
 def test_api_errors(api):
     halmd_b200, simulation = api
     from halmd_b200 import mdsim, HxError

@@ -98,6 +98,44 @@ def test_lj_tables_gpu_functor_float(oracle, trunc):
                                                    1e-30), (trunc, pair, r, e.value, en)
 
 
+def test_hard_core_adapter_closed_form(oracle):
+    """adapters/hard_core_kernel.hpp:66-76 over lennard_jones, sharp truncation: U(r) = 4 eps [(sigma / (r - r_core))^12
+    - (sigma / (r - r_core))^6], fval = -U'(r) / r, evaluated in double; tolerance of the reference's adapter test
+    (power_law_hard_core.cpp:155-160: eps * n * (1 + r / (r - r_core)), n = 12 here, float functor)."""
+    eps, sigma, core, cut = [1.0, 0.5, 0.5, 0.25], [1.0, 2.0, 2.0, 4.0], [0.375, 0.5, 0.5, 0.75], [5.0, 6.0, 6.0, 7.0]
+    p = support.OLjParams()
+    oracle.oracle_lj_init_hard_core(C.byref(p), 2, 2, support.farr(eps), support.farr(sigma), support.farr(core), 0,
+                                    support.farr(cut), C.c_float(0))
+    assert p.hard_core == 1
+    for idx in (0, 1, 3):
+        e_, s_, rc_ = eps[idx], sigma[idx], core[idx] * sigma[idx]
+        assert p.r_core[idx] == np.float32(core[idx]) * np.float32(sigma[idx])
+        for x in (0.5, 0.8, 1.0, 1.12, 1.5, 2.0, 3.0, 4.5):
+            r = rc_ + x * s_
+            f, e = C.c_float(), C.c_float()
+            rr = np.float32(r) * np.float32(r)
+            assert oracle.oracle_pair_f(C.byref(p), idx, C.c_float(rr), C.byref(f), C.byref(e))
+            r_ = float(np.sqrt(np.float64(rr)))
+            q6 = (s_ / (r_ - rc_)) ** 6
+            en = 4 * e_ * (q6 * q6 - q6)
+            fval = 24 * e_ * (2 * q6 * q6 - q6) / (r_ - rc_) / r_
+            tol = 14 * EPS_F * (1 + r / (r - rc_))
+            # (absolute scale of the two competing terms: the force changes sign at 2^(1/6) sigma)
+            assert abs(f.value - fval) <= tol * max(abs(fval), 24 * e_ * q6 / (r_ - rc_) / r_), (idx, x, f.value, fval)
+            assert abs(e.value - en) <= tol * max(abs(en), 4 * e_ * q6), (idx, x, e.value, en)
+    # shifted / force-shifted tables use the adapted potential at the cutoff (shifted.hpp, force_shifted.hpp:69-70)
+    oracle.oracle_lj_init_hard_core(C.byref(p), 2, 2, support.farr(eps), support.farr(sigma), support.farr(core), 3,
+                                    support.farr(cut), C.c_float(0))
+    rc_, r_c = core[0] * sigma[0], cut[0] * sigma[0]
+    q6 = (sigma[0] / (r_c - rc_)) ** 6
+    assert abs(p.en_cut[0] - 4 * eps[0] * (q6 * q6 - q6)) < 1e-5 * abs(4 * eps[0] * q6)
+    assert abs(p.force_cut[0] - 24 * eps[0] * (2 * q6 * q6 - q6) / (r_c - rc_)) < 1e-5 * abs(24 * eps[0] * q6 / (r_c - rc_))
+    f, e = C.c_float(), C.c_float()
+    assert not oracle.oracle_pair_f(C.byref(p), 0, C.c_float(np.float32(r_c) ** 2), C.byref(f), C.byref(e))
+    assert oracle.oracle_pair_f(C.byref(p), 0, C.c_float(np.float32(r_c * (1 - 1e-4)) ** 2), C.byref(f), C.byref(e))
+    assert abs(f.value) < 1e-3 * abs(p.force_cut[0]) and abs(e.value) < 1e-6     # force and energy vanish at the cutoff
+
+
 def test_lj_init_tables(oracle):
     """Derived tables as in lennard_jones.cpp:52-70 / smooth_r4.hpp:55-91, KA mixture parameters."""
     eps = [1.0, 1.5, 1.5, 0.5]
