@@ -419,8 +419,23 @@ static int pair_force_impl(int truncation, unsigned ntype, const float* epsilon,
     lj::lennard_jones const plain(t_lj.t);
     int rc;
     if (r_core) {
-        potentials::pair::adapters::hard_core_kernel::hard_core<lj::lennard_jones> const adapted(plain, t_core.t);
-        rc = run(adapted);
+        // In this version of the reference the force kernels call potential.fetch_param() (pair_trunc_kernel.cuh:118),
+        // which hard_core does not override: its fetch() (hard_core_kernel.cuh:37-44, the only place that reads the
+        // core-radius texture) is never called and r_core_ keeps whatever the host-side functor object contained when
+        // it was passed as a kernel argument.  The harness therefore stores the radius the host class uploads
+        // (adapters/hard_core.hpp:60-72) into that member before the launch — one value for all species pairs, since
+        // nothing in the kernel could select another — through a layout-identical mirror of the private members.
+        typedef potentials::pair::adapters::hard_core_kernel::hard_core<lj::lennard_jones> adapted_type;
+        struct mirror : lj::lennard_jones {
+            mirror(lj::lennard_jones const& p) : lj::lennard_jones(p) {}
+            float r_core;
+            cudaTextureObject_t t_param;
+        };
+        static_assert(sizeof(mirror) == sizeof(adapted_type), "hard_core layout");
+        for (unsigned t = 1; t < np; ++t) if (h_core[t] != h_core[0]) return static_cast<int>(cudaErrorInvalidValue);
+        adapted_type adapted(plain, t_core.t);
+        reinterpret_cast<mirror&>(adapted).r_core = h_core[0];
+        rc = run(static_cast<adapted_type const&>(adapted));
     } else {
         rc = run(plain);
     }

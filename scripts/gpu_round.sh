@@ -6,14 +6,15 @@ out=gpurun_out
 mkdir -p $out
 (timeout 1000 python -m pytest tests -m gpu -q 2>&1 | tail -6) > $out/${tag}_pytest_gpu.log
 B="python bench.py --steps 1 --warmup 1 --md-steps 300 --melt-steps 600 --no-cpu-baseline"
-# launches: melt 600 steps (~1900 launches incl. rebuilds), then 2 x 300 NVE steps; list the last ~700 launches
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 2600 -c 700 --csv \
+# launches: melt 600 Andersen steps (4 launches per step + rebuilds, ~4200 in all), then 2 x 300 NVE steps (2 launches per
+# step + 14 per rebuild); list ~900 launches of the NVE part
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 4300 -c 900 --csv \
     --log-file $out/${tag}_launches.csv $B > $out/${tag}_launches.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_force_row2 -s 1500 -c 1 \
     -f -o $out/${tag}_force $B > $out/${tag}_force_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_nlist_build -s 40 -c 1 \
     -f -o $out/${tag}_nlist $B > $out/${tag}_nlist_ncu.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_verlet -s 700 -c 1 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_verlet -s 900 -c 1 \
     -f -o $out/${tag}_verlet $B > $out/${tag}_verlet_ncu.log 2>&1
 (timeout 600 python bench.py 2>&1 | tail -1) > $out/${tag}_bench.json
 (timeout 600 python bench.py --impl reference 2>&1 | tail -1) > $out/${tag}_bench_reference.json
