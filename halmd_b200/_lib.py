@@ -37,6 +37,11 @@ class LjParams(C.Structure):
 MAX_WALLS, MAX_WALL_SPECIES = 8, 4
 
 
+class HooverChain(C.Structure):
+    _fields_ = [("xi", C.c_double * 2), ("v_xi", C.c_double * 2), ("mass_xi", C.c_double * 2),
+                ("temperature", C.c_double), ("en_kin_target_2", C.c_double), ("dof", C.c_double)]
+
+
 class PlanarWall(C.Structure):
     _fields_ = [
         ("nwall", C.c_uint), ("nspecies", C.c_uint), ("smoothing", C.c_float),
@@ -105,6 +110,10 @@ _protos = {
     "hx_andersen_finalize": (C.c_int, [P, P, SZ, SZ, C.c_float, C.c_float, C.c_float, C.POINTER(Rand48), P, P]),
     "hx_hoover_integrate": (C.c_int, [P, P, P, P, SZ, C.c_float, C.c_double, F3, P]),
     "hx_hoover_rescale": (C.c_int, [P, SZ, C.c_double, P]),
+    "hx_hoover_chain_init": (C.c_int, [C.POINTER(HooverChain), SZ, C.c_uint, C.c_double, C.c_double]),
+    "hx_hoover_chain_set_temperature": (C.c_int, [C.POINTER(HooverChain), C.c_double, C.c_double]),
+    "hx_hoover_chain_propagate": (C.c_double, [C.POINTER(HooverChain), C.c_double, C.c_double]),
+    "hx_hoover_chain_energy": (C.c_double, [C.POINTER(HooverChain), SZ]),
     "hx_andersen_scratch_bytes": (SZ, [SZ]),
     "hx_andersen_finalize2": (C.c_int, [P, P, SZ, SZ, C.c_float, C.c_float, C.c_float, C.POINTER(Rand48), P, P, SZ, P, P]),
     "hx_andersen_finalize_guarded": (C.c_int, [P, P, SZ, SZ, C.c_float, C.c_float, C.c_float,

@@ -184,4 +184,66 @@ int hx_potential_lj_init_hard_core(hx_lj_params* p, unsigned ntype1, unsigned nt
     return HX_OK;
 }
 
+/* ---- Nose-Hoover chain, host side (verlet_nvt_hoover.cpp:79-95, :175-222) ---------------------------------------- */
+int hx_hoover_chain_set_temperature(hx_hoover_chain* c, double temperature, double resonance_frequency)
+{
+    if (!c || !(temperature > 0) || !(resonance_frequency > 0)) {
+        set_error("hx_hoover_chain_set_temperature: invalid argument");
+        return HX_E_INVALID;
+    }
+    c->temperature = temperature;
+    c->en_kin_target_2 = c->dof * temperature;
+    // follow Martyna et al. [J. Chem. Phys. 97, 2635 (1992)] for the masses
+    double const omega_sq = std::pow(2 * M_PI * resonance_frequency, 2);
+    c->mass_xi[0] = c->dof * temperature / omega_sq;
+    c->mass_xi[1] = temperature / omega_sq;
+    return HX_OK;
+}
+
+int hx_hoover_chain_init(hx_hoover_chain* c, size_t nparticle, unsigned dimension, double temperature,
+                         double resonance_frequency)
+{
+    if (!c || nparticle == 0 || dimension == 0) {
+        set_error("hx_hoover_chain_init: invalid argument");
+        return HX_E_INVALID;
+    }
+    std::memset(c, 0, sizeof(*c));
+    c->dof = static_cast<double>(dimension) * static_cast<double>(nparticle);
+    return hx_hoover_chain_set_temperature(c, temperature, resonance_frequency);
+}
+
+double hx_hoover_chain_propagate(hx_hoover_chain* c, double en_kin_2, double timestep)
+{
+    double const dt2 = timestep / 2, dt4 = timestep / 4, dt8 = timestep / 8;
+    double* const xi = c->xi;
+    double* const v = c->v_xi;
+    double const* const m = c->mass_xi;
+    double const T = c->temperature;
+    // head of the chain
+    v[1] += (m[0] * v[0] * v[0] - T) / m[1] * dt4;
+    double const t = std::exp(-v[1] * dt8);
+    v[0] *= t;
+    v[0] += (en_kin_2 - c->en_kin_target_2) / m[0] * dt4;
+    v[0] *= t;
+    // heat-bath positions
+    xi[0] += v[0] * dt2;
+    xi[1] += v[1] * dt2;
+    // the factor the kernels apply to the velocities; the kinetic energy follows with its square
+    double const s = std::exp(-v[0] * dt2);
+    en_kin_2 *= s * s;
+    // tail of the chain, mirror image of the head
+    v[0] *= t;
+    v[0] += (en_kin_2 - c->en_kin_target_2) / m[0] * dt4;
+    v[0] *= t;
+    v[1] += (m[0] * v[0] * v[0] - T) / m[1] * dt4;
+    return s;
+}
+
+double hx_hoover_chain_energy(const hx_hoover_chain* c, size_t nparticle)
+{
+    double en = c->temperature * (c->dof * c->xi[0] + c->xi[1]);
+    for (int i = 0; i < 2; ++i) en += c->mass_xi[i] * c->v_xi[i] * c->v_xi[i] / 2;
+    return en / static_cast<double>(nparticle);
+}
+
 } // extern "C"

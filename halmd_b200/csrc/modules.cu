@@ -349,9 +349,9 @@ struct hxm_integrator {
     hx_rand48 rng;
     uint16_t* rng_state = nullptr;
     unsigned char* andersen_scratch = nullptr;
-    // Nose-Hoover chain (verlet_nvt_hoover.hpp:100-160): chain positions / velocities / masses, derived time steps
-    double xi[2] = {0, 0}, v_xi[2] = {0, 0}, mass_xi[2] = {1, 1};
-    double resonance_frequency = 5, en_kin_target_2 = 0, en_nhc = 0;
+    // Nose-Hoover chain (verlet_nvt_hoover.hpp:100-160): heat-bath variables on the host
+    hx_hoover_chain chain = {};
+    double resonance_frequency = 5, en_nhc = 0;
     double* d_hoover = nullptr;      // device / pinned scratch of the kinetic-energy reduction
     double* h_hoover = nullptr;
 
@@ -361,16 +361,6 @@ struct hxm_integrator {
         if (h_hoover) cudaFreeHost(h_hoover);
     }
 
-    // verlet_nvt_hoover::set_temperature (verlet_nvt_hoover.cpp:79-95): masses after Martyna et al.
-    void update_hoover()
-    {
-        double const dof = 3.0 * static_cast<double>(particle->n);
-        en_kin_target_2 = dof * temperature;
-        double const omega_sq = std::pow(2 * M_PI * resonance_frequency, 2);
-        mass_xi[0] = dof * temperature / omega_sq;
-        mass_xi[1] = temperature / omega_sq;
-    }
-
     // verlet_nvt_hoover::propagate_chain (verlet_nvt_hoover.cpp:185-222): returns the velocity scale factor
     int propagate_chain(double* scale)
     {
@@ -378,21 +368,8 @@ struct hxm_integrator {
         HXM_TRY(hx_thermodynamics(reinterpret_cast<hx_float4*>(p->vel), nullptr, nullptr, p->A, p->n, d_hoover, p->st));
         HXM_CUDA(cudaMemcpyAsync(h_hoover, d_hoover, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->st));
         HXM_CUDA(cudaStreamSynchronize(p->st));
-        double en_kin_2 = h_hoover[0];          // sum m v^2 = 2 E_kin
-        double const dt4 = timestep / 4, dt8 = timestep / 8, dt2 = timestep / 2;
-        v_xi[1] += (mass_xi[0] * v_xi[0] * v_xi[0] - temperature) / mass_xi[1] * dt4;
-        double const t = std::exp(-v_xi[1] * dt8);
-        v_xi[0] *= t;
-        v_xi[0] += (en_kin_2 - en_kin_target_2) / mass_xi[0] * dt4;
-        v_xi[0] *= t;
-        for (int i = 0; i < 2; ++i) xi[i] += v_xi[i] * dt2;
-        double const s = std::exp(-v_xi[0] * dt2);
-        en_kin_2 *= s * s;
-        v_xi[0] *= t;
-        v_xi[0] += (en_kin_2 - en_kin_target_2) / mass_xi[0] * dt4;
-        v_xi[0] *= t;
-        v_xi[1] += (mass_xi[0] * v_xi[0] * v_xi[0] - temperature) / mass_xi[1] * dt4;
-        *scale = s;
+        // sum m v^2 = 2 E_kin of all particles drives the chain
+        *scale = hx_hoover_chain_propagate(&chain, h_hoover[0], timestep);
         return 0;
     }
 
@@ -436,10 +413,7 @@ struct hxm_integrator {
             double scale = 1;
             HXM_TRY(propagate_chain(&scale));
             HXM_TRY(hx_hoover_rescale(reinterpret_cast<hx_float4*>(p->vel), p->A, scale, p->st));
-            double const N = static_cast<double>(p->n);
-            en_nhc = temperature * (3.0 * N * xi[0] + xi[1]);
-            for (int i = 0; i < 2; ++i) en_nhc += mass_xi[i] * v_xi[i] * v_xi[i] / 2;
-            en_nhc /= N;
+            en_nhc = hx_hoover_chain_energy(&chain, p->n);
             return 0;
         }
         if (kind == VERLET) {
@@ -1184,8 +1158,8 @@ int hxm_integrator_set_temperature(hxm_integrator* i, double temperature)
 {
     if (!i || !(temperature >= 0)) return HX_E_INVALID;
     i->temperature = temperature;
-    if (i->kind == hxm_integrator::HOOVER) i->update_hoover();
-    else i->update_andersen();
+    if (i->kind == hxm_integrator::HOOVER) return hx_hoover_chain_set_temperature(&i->chain, temperature, i->resonance_frequency);
+    i->update_andersen();
     return 0;
 }
 
@@ -1198,7 +1172,7 @@ int hxm_integrator_hoover_create(hxm_particle* particle, hxm_force* force, const
     std::unique_ptr<hxm_integrator> guard(i);
     i->temperature = temperature;
     i->resonance_frequency = resonance_frequency;
-    i->update_hoover();
+    HXM_TRY(hx_hoover_chain_init(&i->chain, particle->n, 3, temperature, resonance_frequency));
     HXM_TRY(dev_alloc(&i->d_hoover, 8));
     HXM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&i->h_hoover), 8 * sizeof(double)));
     *out = guard.release();
@@ -1208,8 +1182,8 @@ int hxm_integrator_hoover_create(hxm_particle* particle, hxm_force* force, const
 int hxm_integrator_hoover_set_mass(hxm_integrator* i, const double mass[2])
 {
     if (!i || !mass || i->kind != hxm_integrator::HOOVER || !(mass[0] > 0) || !(mass[1] > 0)) return HX_E_INVALID;
-    i->mass_xi[0] = mass[0];
-    i->mass_xi[1] = mass[1];
+    i->chain.mass_xi[0] = mass[0];
+    i->chain.mass_xi[1] = mass[1];
     return 0;
 }
 
@@ -1217,8 +1191,8 @@ int hxm_integrator_hoover_set_mass(hxm_integrator* i, const double mass[2])
 int hxm_integrator_hoover_state(const hxm_integrator* i, double out[7])
 {
     if (!i || !out || i->kind != hxm_integrator::HOOVER) return HX_E_INVALID;
-    out[0] = i->xi[0]; out[1] = i->xi[1]; out[2] = i->v_xi[0]; out[3] = i->v_xi[1];
-    out[4] = i->mass_xi[0]; out[5] = i->mass_xi[1]; out[6] = i->en_nhc;
+    out[0] = i->chain.xi[0]; out[1] = i->chain.xi[1]; out[2] = i->chain.v_xi[0]; out[3] = i->chain.v_xi[1];
+    out[4] = i->chain.mass_xi[0]; out[5] = i->chain.mass_xi[1]; out[6] = i->en_nhc;
     return 0;
 }
 

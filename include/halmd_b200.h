@@ -242,6 +242,20 @@ int hx_hoover_integrate(hx_float4* position_dev, hx_float4* image_dev, hx_float4
                         const hx_float4* force_dev, size_t array_size, float timestep, double scale,
                         const float box_length[3], void* stream);
 int hx_hoover_rescale(hx_float4* velocity_dev, size_t array_size, double scale, void* stream);
+/* Host side of the thermostat (no device work): the chain of two heat-bath variables of
+ * verlet_nvt_hoover.hpp:100-160.  init: set_temperature (verlet_nvt_hoover.cpp:79-95), masses
+ * (dof T / omega^2, T / omega^2) with omega = 2 pi resonance_frequency, dof = dimension * nparticle, chain at rest.
+ * propagate: propagate_chain (verlet_nvt_hoover.cpp:185-222) for en_kin_2 = sum m v^2 over all particles; returns the
+ * velocity scale factor.  energy: en_nhc per particle (verlet_nvt_hoover.cpp:175-182). */
+typedef struct hx_hoover_chain {
+    double xi[2], v_xi[2], mass_xi[2];
+    double temperature, en_kin_target_2, dof;
+} hx_hoover_chain;
+int hx_hoover_chain_init(hx_hoover_chain* chain, size_t nparticle, unsigned dimension, double temperature,
+                         double resonance_frequency);
+int hx_hoover_chain_set_temperature(hx_hoover_chain* chain, double temperature, double resonance_frequency);
+double hx_hoover_chain_propagate(hx_hoover_chain* chain, double en_kin_2, double timestep);
+double hx_hoover_chain_energy(const hx_hoover_chain* chain, size_t nparticle);
 
 /* ---- a13: Andersen thermostat with rand48 ---------------------------------------------------
  * halmd/random/gpu/rand48.hpp:57-81, rand48_kernel.cu:42-100, rand48_kernel.cuh:40-79,

@@ -582,6 +582,97 @@ void oracle_verlet_integrate(f4* pos, f4* image, f4* vel, const f4* force, size_
     }
 }
 
+/* ---- Nose-Hoover chain: halmd/mdsim/gpu/integrators/verlet_nvt_hoover_kernel.cu:37-125 (kernels),
+ * verlet_nvt_hoover.cpp:79-95, :175-222 (host-side chain) --------------------------------------------------------- */
+
+/* v *= scale for dsfloat operands as the reference build executes dsmul (dsfun.hpp:178-207 under --fmad=true): the
+ * cross term a0 * b1 + a1 * b0 and the low-order product ride on fused multiply-adds; the Dekker part is exact either
+ * way, so only these two contractions are visible in the result */
+static inline ds ds_mul_gpu(ds a, ds b)
+{
+    float cona = a.hi * 8193.0f;
+    float conb = b.hi * 8193.0f;
+    float sa1 = cona - (cona - a.hi);
+    float sb1 = conb - (conb - b.hi);
+    float sa2 = a.hi - sa1;
+    float sb2 = b.hi - sb1;
+    float c11 = a.hi * b.hi;
+    float c21 = (((sa1 * sb1 - c11) + sa1 * sb2) + sa2 * sb1) + sa2 * sb2;
+    float c2 = fmaf(a.hi, b.lo, a.lo * b.hi);
+    float t1 = c11 + c2;
+    float e = t1 - c11;
+    float t2 = fmaf(a.lo, b.lo, c21 + ((c2 - e) + (c11 - (t1 - e))));
+    ds c;
+    c.hi = t1 + t2;
+    c.lo = t2 - (c.hi - t1);
+    return c;
+}
+
+/* dsfloat(double): dsfloat.hpp — hi = float(a), lo = float(a - hi) */
+static inline ds ds_from_double(double a)
+{
+    ds r;
+    r.hi = (float)a;
+    r.lo = (float)(a - (double)r.hi);
+    return r;
+}
+
+void oracle_hoover_rescale(f4* vel, size_t A, double scale)
+{
+    ds s = ds_from_double(scale);
+    for (size_t i = 0; i < A; ++i) {
+        ds vx = ds_mul_gpu(mkds(vel[i].x, vel[i + A].x), s);
+        ds vy = ds_mul_gpu(mkds(vel[i].y, vel[i + A].y), s);
+        ds vz = ds_mul_gpu(mkds(vel[i].z, vel[i + A].z), s);
+        vel[i].x = vx.hi; vel[i].y = vy.hi; vel[i].z = vz.hi;
+        vel[i + A].x = vx.lo; vel[i + A].y = vy.lo; vel[i + A].z = vz.lo; vel[i + A].w = 0;
+    }
+}
+
+void oracle_hoover_integrate(f4* pos, f4* image, f4* vel, const f4* force, size_t A, float dt, double scale, const float L[3])
+{
+    oracle_hoover_rescale(vel, A, scale);
+    oracle_verlet_integrate(pos, image, vel, force, A, dt, L);
+}
+
+typedef struct { double xi[2], v_xi[2], mass_xi[2], temperature, en_kin_target_2, dof; } hoover_chain;
+
+void oracle_hoover_chain_init(hoover_chain* c, size_t nparticle, unsigned dimension, double temperature, double resonance_frequency)
+{
+    memset(c, 0, sizeof(*c));
+    c->dof = (double)dimension * (double)nparticle;
+    c->temperature = temperature;
+    c->en_kin_target_2 = c->dof * temperature;
+    double omega_sq = pow(2 * M_PI * resonance_frequency, 2);
+    c->mass_xi[0] = c->dof * temperature / omega_sq;
+    c->mass_xi[1] = temperature / omega_sq;
+}
+
+double oracle_hoover_chain_propagate(hoover_chain* c, double en_kin_2, double timestep)
+{
+    double timestep_half = timestep / 2, timestep_4 = timestep / 4, timestep_8 = timestep / 8;
+    c->v_xi[1] += (c->mass_xi[0] * c->v_xi[0] * c->v_xi[0] - c->temperature) / c->mass_xi[1] * timestep_4;
+    double t = exp(-c->v_xi[1] * timestep_8);
+    c->v_xi[0] *= t;
+    c->v_xi[0] += (en_kin_2 - c->en_kin_target_2) / c->mass_xi[0] * timestep_4;
+    c->v_xi[0] *= t;
+    for (int i = 0; i < 2; ++i) c->xi[i] += c->v_xi[i] * timestep_half;
+    double s = exp(-c->v_xi[0] * timestep_half);
+    en_kin_2 *= s * s;
+    c->v_xi[0] *= t;
+    c->v_xi[0] += (en_kin_2 - c->en_kin_target_2) / c->mass_xi[0] * timestep_4;
+    c->v_xi[0] *= t;
+    c->v_xi[1] += (c->mass_xi[0] * c->v_xi[0] * c->v_xi[0] - c->temperature) / c->mass_xi[1] * timestep_4;
+    return s;
+}
+
+double oracle_hoover_chain_energy(const hoover_chain* c, size_t nparticle)
+{
+    double en = c->temperature * (c->dof * c->xi[0] + c->xi[1]);
+    for (int i = 0; i < 2; ++i) en += c->mass_xi[i] * c->v_xi[i] * c->v_xi[i] / 2;
+    return en / (double)nparticle;
+}
+
 /* ---- rand48: halmd/random/gpu/rand48_kernel.cu:42-100, rand48_kernel.cuh:40-79, uint48.hpp:72-111 ------------ */
 #define R48_MASK ((1ull << 48) - 1)
 #define R48_A 0x5DEECE66Dull

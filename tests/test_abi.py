@@ -5,6 +5,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 import support
 
@@ -79,6 +80,33 @@ def test_hard_core_tables_match_oracle(hx, oracle):
     p = hx.LjParams()
     assert hx.lib.hx_potential_lj_init_hard_core(C.byref(p), 1, 1, hx.farr([1.0]), hx.farr([1.0]), hx.farr([2.5]), 1,
                                                  hx.farr([2.5]), 0.0) < 0       # core radius beyond the cutoff
+
+
+def test_hoover_chain_matches_oracle(hx, oracle):
+    """Host side of the Nose-Hoover thermostat in the product library against the oracle's restatement of
+    verlet_nvt_hoover.cpp:79-95, :175-222: identical chain trajectories (bit for bit) for a fluctuating kinetic energy."""
+    from test_oracle_properties import OHooverChain
+    oracle.oracle_hoover_chain_propagate.restype = C.c_double
+    oracle.oracle_hoover_chain_energy.restype = C.c_double
+    n, T, fres, dt = 4000, 0.7, 3.0, 0.005
+    a, b = hx.HooverChain(), OHooverChain()
+    hx.check(hx.lib.hx_hoover_chain_init(C.byref(a), n, 3, T, fres))
+    oracle.oracle_hoover_chain_init(C.byref(b), C.c_size_t(n), 3, C.c_double(T), C.c_double(fres))
+    assert bytes(a) == bytes(b)
+    rng = np.random.default_rng(8)
+    ek = 3 * n * 2.0
+    for _ in range(2000):
+        sa = hx.lib.hx_hoover_chain_propagate(C.byref(a), ek, dt)
+        sb = oracle.oracle_hoover_chain_propagate(C.byref(b), C.c_double(ek), C.c_double(dt))
+        assert sa == sb
+        ek = ek * sa * sa * (1 + 0.01 * rng.normal())
+    assert bytes(a) == bytes(b)
+    assert hx.lib.hx_hoover_chain_energy(C.byref(a), n) == oracle.oracle_hoover_chain_energy(C.byref(b), C.c_size_t(n))
+    assert abs(ek / (3 * n) - T) < 0.2 * T                      # the thermostat pulled the temperature to the target
+    hx.check(hx.lib.hx_hoover_chain_set_temperature(C.byref(a), 2 * T, fres))
+    assert a.mass_xi[1] == pytest.approx(2 * T / (2 * np.pi * fres) ** 2, rel=1e-15) and a.en_kin_target_2 == 3 * n * 2 * T
+    assert hx.lib.hx_hoover_chain_init(C.byref(a), 0, 3, T, fres) < 0
+    assert hx.lib.hx_hoover_chain_set_temperature(C.byref(a), -1.0, fres) < 0
 
 
 def test_planar_wall_tables_match_oracle(hx):

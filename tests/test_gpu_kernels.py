@@ -449,6 +449,39 @@ def test_pair_potential_golden_chain(hx, oracle, dev):
 
 # ---- a12 velocity-Verlet ------------------------------------------------------------------------------------------
 
+def test_hoover_kernels_bit_exact(hx, oracle, dev):
+    """Nose-Hoover integrate(scale) / rescale(scale) against the oracle (verlet_nvt_hoover_kernel.cu:37-125): the
+    double-single product v * scale with both low words live, then the Verlet half-step — hi and lo words, images."""
+    n = 20000
+    L, p, v, A = lj_fluid(n, 0.8442, 43)
+    rng = np.random.default_rng(43)
+    v[:n, :3] *= 30
+    v[:n, 3] = rng.choice([1.0, 2.0, 0.5], n)
+    v[A:A + n, :3] = (rng.normal(size=(n, 3)) * 1e-7).astype(np.float32)
+    f = np.zeros((A, 4), dtype=np.float32)
+    f[:n, :3] = rng.normal(scale=20, size=(n, 3))
+    img = np.zeros((A, 4), dtype=np.float32)
+    dt = 0.005
+    d_p, d_v, d_f, d_i = dev.up(p), dev.up(v), dev.up(f), dev.up(img)
+    op, ov, oi = p.copy(), v.copy(), img.copy()
+    for scale in (0.9991234567891234, 1.0004321098765432, 1.0, 0.75):
+        hx.check(hx.lib.hx_hoover_integrate(dev.p(d_p), dev.p(d_i), dev.p(d_v), dev.p(d_f), A, dt, scale, hx.f3(L), dev.stream))
+        hx.check(hx.lib.hx_verlet_finalize(dev.p(d_v), dev.p(d_f), A, dt, dev.stream))
+        hx.check(hx.lib.hx_hoover_rescale(dev.p(d_v), A, scale, dev.stream))
+        oracle.oracle_hoover_integrate(support.ptr(op), support.ptr(oi), support.ptr(ov), support.ptr(f), C.c_size_t(A),
+                                       C.c_float(dt), C.c_double(scale), support.f3(L))
+        oracle.oracle_verlet_finalize(support.ptr(ov), support.ptr(f), C.c_size_t(A), C.c_float(dt))
+        oracle.oracle_hoover_rescale(support.ptr(ov), C.c_size_t(A), C.c_double(scale))
+    gp, gv, gi = dev.down(d_p), dev.down(d_v), dev.down(d_i)
+    for name, got, exp in (("velocity", gv, ov), ("position", gp, op), ("image", gi, oi)):
+        bad = np.argwhere((got[:n].view(np.uint32) != exp[:n].view(np.uint32)) & ~((got[:n] == 0) & (exp[:n] == 0)))
+        assert bad.size == 0, (name, len(bad), bad[:4].tolist())
+        bad = np.argwhere((got[A:A + n].view(np.uint32) != exp[A:A + n].view(np.uint32)) & ~((got[A:A + n] == 0) & (exp[A:A + n] == 0))) \
+            if name != "image" else np.zeros(0)
+        assert bad.size == 0, (name + " (low words)", len(bad))
+    assert np.abs(gi[:n, :3]).max() >= 1
+
+
 def test_verlet_bit_exact(hx, oracle, dev):
     """Double-single integrate/finalize: hi AND lo words equal the oracle's bit for bit, including periodic wrap
     and image bookkeeping; the fused kernel equals the separate calls."""

@@ -219,6 +219,76 @@ def test_verlet_ideal_gas(oracle):
     assert np.abs(p[:n, :3]).max() <= 5.0 + 1e-6
 
 
+class OHooverChain(C.Structure):
+    _fields_ = [("xi", C.c_double * 2), ("v_xi", C.c_double * 2), ("mass_xi", C.c_double * 2),
+                ("temperature", C.c_double), ("en_kin_target_2", C.c_double), ("dof", C.c_double)]
+
+
+def test_hoover_kernels_properties(oracle):
+    """verlet_nvt_hoover_kernel.cu:37-125 restated: with scale = 1 the integrate step IS the plain Verlet step; a
+    power-of-two scale is exact in both words; a general scale agrees with the product formed in double to
+    double-single accuracy (2^-44)."""
+    rng = np.random.default_rng(5)
+    n = 2000
+    L = np.array([12.0, 12.0, 12.0])
+    p, v, A = support.pack_state(rng.uniform(-6, 6, (n, 3)), vel=rng.normal(size=(n, 3)))
+    img = np.zeros((A, 4), dtype=np.float32)
+    f = np.zeros((A, 4), dtype=np.float32)
+    f[:n, :3] = rng.normal(scale=10, size=(n, 3))
+    dt = C.c_float(0.002)
+    p1, v1, i1 = p.copy(), v.copy(), img.copy()
+    p2, v2, i2 = p.copy(), v.copy(), img.copy()
+    oracle.oracle_hoover_integrate(support.ptr(p1), support.ptr(i1), support.ptr(v1), support.ptr(f), C.c_size_t(A), dt,
+                                   C.c_double(1.0), support.f3(L))
+    oracle.oracle_verlet_integrate(support.ptr(p2), support.ptr(i2), support.ptr(v2), support.ptr(f), C.c_size_t(A), dt,
+                                   support.f3(L))
+    assert p1.tobytes() == p2.tobytes() and v1.tobytes() == v2.tobytes() and i1.tobytes() == i2.tobytes()
+    w = v.copy()
+    oracle.oracle_hoover_rescale(support.ptr(w), C.c_size_t(A), C.c_double(0.5))
+    assert np.array_equal(w[:n, :3], v[:n, :3] * np.float32(0.5)) and np.array_equal(w[A:A + n, :3], v[A:A + n, :3] * np.float32(0.5))
+    assert np.array_equal(w[:n, 3], v[:n, 3])                                  # masses untouched
+    scale = 0.9987654321012345
+    w = v.copy()
+    oracle.oracle_hoover_rescale(support.ptr(w), C.c_size_t(A), C.c_double(scale))
+    got = w[:n, :3].astype(np.float64) + w[A:A + n, :3]
+    want = (v[:n, :3].astype(np.float64) + v[A:A + n, :3]) * scale
+    assert np.abs(got - want).max() <= 2.0 ** -43 * np.abs(want).max()
+    assert np.all(np.abs(w[A:A + n, :3]) <= np.spacing(np.abs(w[:n, :3])) / 2 * (1 + 1e-6))      # normalised double-single
+
+
+def test_hoover_chain_properties(oracle):
+    """verlet_nvt_hoover.cpp:79-95, :185-222: chain masses after Martyna et al.; a system exactly at the target kinetic
+    energy with the chain at rest is a fixed point (scale = 1); a hot system is damped, a cold one heated; the two
+    half-step propagations of a step are mirror images, so stepping back with -dt restores the chain."""
+    n, T, fres, dt = 1500, 1.0, 5.0, 0.002
+    c = OHooverChain()
+    oracle.oracle_hoover_chain_propagate.restype = C.c_double
+    oracle.oracle_hoover_chain_energy.restype = C.c_double
+    oracle.oracle_hoover_chain_init(C.byref(c), C.c_size_t(n), 3, C.c_double(T), C.c_double(fres))
+    omega_sq = (2 * np.pi * fres) ** 2
+    assert c.mass_xi[0] == pytest.approx(3 * n * T / omega_sq, rel=1e-15) and c.mass_xi[1] == pytest.approx(T / omega_sq, rel=1e-15)
+    assert c.en_kin_target_2 == 3 * n * T
+    s = oracle.oracle_hoover_chain_propagate(C.byref(c), C.c_double(3 * n * T), C.c_double(dt))
+    # at the target the first variable stays at rest; only the second feels -T / m1 (its own thermal drive)
+    assert s == 1.0 and c.v_xi[0] == 0.0 and c.xi[0] == 0.0 and c.v_xi[1] < 0
+    oracle.oracle_hoover_chain_init(C.byref(c), C.c_size_t(n), 3, C.c_double(T), C.c_double(fres))
+    hot = [oracle.oracle_hoover_chain_propagate(C.byref(c), C.c_double(3 * n * 3.0), C.c_double(dt)) for _ in range(20)]
+    assert all(x < 1 for x in hot) and hot[-1] < hot[0]
+    assert oracle.oracle_hoover_chain_energy(C.byref(c), C.c_size_t(n)) > 0
+    oracle.oracle_hoover_chain_init(C.byref(c), C.c_size_t(n), 3, C.c_double(T), C.c_double(fres))
+    cold = [oracle.oracle_hoover_chain_propagate(C.byref(c), C.c_double(3 * n * 0.3), C.c_double(dt)) for _ in range(20)]
+    assert all(x > 1 for x in cold)
+    # time reversal of one propagation at constant kinetic energy scaled consistently
+    oracle.oracle_hoover_chain_init(C.byref(c), C.c_size_t(n), 3, C.c_double(T), C.c_double(fres))
+    c.v_xi[0], c.v_xi[1], c.xi[0], c.xi[1] = 0.3, -0.2, 0.01, 0.02
+    before = (c.xi[0], c.xi[1], c.v_xi[0], c.v_xi[1])
+    ek = 3 * n * 1.7
+    s = oracle.oracle_hoover_chain_propagate(C.byref(c), C.c_double(ek), C.c_double(dt))
+    s_back = oracle.oracle_hoover_chain_propagate(C.byref(c), C.c_double(ek * s * s), C.c_double(-dt))
+    assert s * s_back == pytest.approx(1.0, abs=1e-14)
+    assert (c.xi[0], c.xi[1], c.v_xi[0], c.v_xi[1]) == pytest.approx(before, abs=1e-13)
+
+
 def test_andersen_statistics(oracle):
     """test/unit/mdsim/integrators/verlet_nvt_andersen.cpp:103-174 (statistical): with rate*dt = 1 every warp
     collides; velocities are N(0, sqrt(T)) and the RNG state advances."""
