@@ -82,11 +82,13 @@ struct hxm_particle {
     // every position lies in the primary cell [-L/2, L/2]: true once an integration step has reduced them, false
     // after positions were written from outside (HX_FORCE_POSITIONS_REDUCED)
     bool reduced = false;
+    double* io_dev = nullptr;        // [3 n] staging of double-precision samples (particle get / set)
 
     ~hxm_particle()
     {
         dev_free(pos); dev_free(vel); dev_free(image); dev_free(force); dev_free(pos_b); dev_free(vel_b);
         dev_free(image_b); dev_free(en_pot); dev_free(stress); dev_free(id); dev_free(rid); dev_free(id_b);
+        dev_free(io_dev);
     }
 };
 
@@ -771,31 +773,45 @@ static int particle_float4_io(hxm_particle* p, float4* dev, bool lo_plane, bool 
     return 0;
 }
 
+// double <-> double-single on the device: one 24-byte-per-particle transfer each way instead of staging both float4
+// planes through the host; the split is dsdeq (dsfun.hpp:122-126), the fourth components (species / mass) stay
+__global__ void k_ds_split(float4* __restrict__ dev, unsigned A, unsigned n, const double* __restrict__ src)
+{
+    unsigned const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double const x = src[3 * i], y = src[3 * i + 1], z = src[3 * i + 2];
+    float const hx_ = static_cast<float>(x), hy = static_cast<float>(y), hz = static_cast<float>(z);
+    float4 h = dev[i];
+    h.x = hx_; h.y = hy; h.z = hz;
+    dev[i] = h;
+    dev[i + A] = make_float4(static_cast<float>(x - hx_), static_cast<float>(y - hy), static_cast<float>(z - hz), 0.f);
+}
+
+__global__ void k_ds_join(const float4* __restrict__ dev, unsigned A, unsigned n, double* __restrict__ dst)
+{
+    unsigned const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 const h = dev[i], l = dev[i + A];
+    dst[3 * i] = static_cast<double>(h.x) + l.x;
+    dst[3 * i + 1] = static_cast<double>(h.y) + l.y;
+    dst[3 * i + 2] = static_cast<double>(h.z) + l.z;
+}
+
 static int particle_ds_io(hxm_particle* p, float4* dev, bool set, double* host)
 {
-    size_t n = p->n, A = p->A;
-    std::vector<float4> hi(n), lo(n);
-    HXM_CUDA(cudaMemcpyAsync(hi.data(), dev, n * sizeof(float4), cudaMemcpyDeviceToHost, p->st));
-    HXM_CUDA(cudaMemcpyAsync(lo.data(), dev + A, n * sizeof(float4), cudaMemcpyDeviceToHost, p->st));
-    HXM_CUDA(cudaStreamSynchronize(p->st));
-    if (!set) {
-        for (size_t i = 0; i < n; ++i) {
-            host[3 * i] = static_cast<double>(hi[i].x) + lo[i].x;
-            host[3 * i + 1] = static_cast<double>(hi[i].y) + lo[i].y;
-            host[3 * i + 2] = static_cast<double>(hi[i].z) + lo[i].z;
-        }
-        return 0;
+    size_t const n = p->n;
+    if (n == 0) return 0;
+    if (!p->io_dev) HXM_TRY(dev_alloc(&p->io_dev, 3 * n));
+    unsigned const blocks = static_cast<unsigned>((n + 255) / 256);
+    if (set) {
+        HXM_CUDA(cudaMemcpyAsync(p->io_dev, host, 3 * n * sizeof(double), cudaMemcpyHostToDevice, p->st));
+        k_ds_split<<<blocks, 256, 0, p->st>>>(dev, static_cast<unsigned>(p->A), static_cast<unsigned>(n), p->io_dev);
+        HXM_CUDA(cudaGetLastError());
+    } else {
+        k_ds_join<<<blocks, 256, 0, p->st>>>(dev, static_cast<unsigned>(p->A), static_cast<unsigned>(n), p->io_dev);
+        HXM_CUDA(cudaGetLastError());
+        HXM_CUDA(cudaMemcpyAsync(host, p->io_dev, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, p->st));
     }
-    for (size_t i = 0; i < n; ++i) {
-        // dsdeq (dsfun.hpp:122-126)
-        const double* h = host + 3 * i;
-        hi[i].x = static_cast<float>(h[0]); lo[i].x = static_cast<float>(h[0] - hi[i].x);
-        hi[i].y = static_cast<float>(h[1]); lo[i].y = static_cast<float>(h[1] - hi[i].y);
-        hi[i].z = static_cast<float>(h[2]); lo[i].z = static_cast<float>(h[2] - hi[i].z);
-        lo[i].w = 0;
-    }
-    HXM_CUDA(cudaMemcpyAsync(dev, hi.data(), n * sizeof(float4), cudaMemcpyHostToDevice, p->st));
-    HXM_CUDA(cudaMemcpyAsync(dev + A, lo.data(), n * sizeof(float4), cudaMemcpyHostToDevice, p->st));
     HXM_CUDA(cudaStreamSynchronize(p->st));
     return 0;
 }
