@@ -44,7 +44,17 @@ using namespace halmd;
 using namespace halmd::mdsim::gpu;
 
 #define RG_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "refgpu: %s: %s\n", #x, cudaGetErrorString(e_)); return static_cast<int>(e_); } } while (0)
-#define RG_TRY(stmt) try { stmt; } catch (std::exception const& e) { fprintf(stderr, "refgpu: %s\n", e.what()); return -1; }
+// every launch block is bracketed by events: refgpu_last_kernel_ms() returns the device time of the last one (the
+// reference's kernels timed on this GPU, scripts/ref_kernel_times.py); uploads and downloads lie outside
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static float g_last_ms = -1.f;
+#define RG_TRY(stmt) try { \
+        if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); } \
+        cudaEventRecord(g_ev0); \
+        stmt; \
+        cudaEventRecord(g_ev1); cudaEventSynchronize(g_ev1); cudaEventElapsedTime(&g_last_ms, g_ev0, g_ev1); \
+    } catch (std::exception const& e) { fprintf(stderr, "refgpu: %s\n", e.what()); return -1; }
+extern "C" float refgpu_last_kernel_ms() { return g_last_ms; }
 
 namespace {
 
