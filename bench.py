@@ -303,7 +303,6 @@ def run_ours(args, cfg):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    hx.check(hx.lib.hx_pair_force_set_lanes(args.lanes))
     decomposed = cfg["kind"] == "lj-dd"
 
     # one GPU: the whole system; several GPUs: one slab of the decomposed system per rank (weak scaling: the

@@ -15,6 +15,13 @@ LIB_PATH = os.environ.get("HALMD_B200_LIB") or os.path.join(_HERE, "libhalmd_b20
 PLACEHOLDER = 0xFFFFFFFF
 LAYOUT_COLUMN, LAYOUT_ROW = 0, 1
 FORCE_POSITIONS_REDUCED = 0x100     # OR-ed into `layout` of the pair-force calls (include/halmd_b200.h)
+FORCE_SCALAR = 0x200
+NSHELL = 8
+
+
+def FORCE_LANES(lanes):
+    return int(lanes) << 12
+
 TRUNC_SHARP, TRUNC_SHIFTED, TRUNC_SMOOTH_R4, TRUNC_FORCE_SHIFTED = 0, 1, 2, 3
 CORR_MSD, CORR_MQD, CORR_VACF = 0, 1, 2
 MAX_PAIR_TYPES = 16
@@ -32,6 +39,10 @@ class LjParams(C.Structure):
         ("en_cut", C.c_float * MAX_PAIR_TYPES), ("force_cut", C.c_float * MAX_PAIR_TYPES),
         ("hard_core", C.c_int), ("r_core", C.c_float * MAX_PAIR_TYPES),
     ]
+
+
+class ShellRows(C.Structure):
+    _fields_ = [("rows_dev", C.c_void_p), ("ends_dev", C.c_void_p), ("pitch", C.c_uint), ("delta", C.c_float * NSHELL)]
 
 
 MAX_WALLS, MAX_WALL_SPECIES = 8, 4
@@ -79,6 +90,7 @@ _protos = {
     "hx_state_init": (C.c_int, [P, P, P, P, P, P, SZ, SZ, P]),
     "hx_binning_plan": (C.c_int, [D3, SZ, C.c_float, C.c_float, C.c_double, U3, F3, U3]),
     "hx_binning_update": (C.c_int, [P, SZ, F3, U3, C.c_uint, P, P, P, P, P]),
+    "hx_device_rcp": (C.c_int, [F3, F3, C.c_uint]),
     "hx_hilbert_depth": (C.c_uint, [D3]),
     "hx_hilbert_keys": (C.c_int, [P, SZ, F3, C.c_uint, P, P]),
     "hx_iota_u32": (C.c_int, [P, SZ, P]),
@@ -99,8 +111,11 @@ _protos = {
     "hx_external_planar_wall": (C.c_int, [C.POINTER(PlanarWall), P, SZ, F3, C.c_int, P, P, P, SZ, P, P]),
     "hx_pair_force_guarded": (C.c_int, [C.POINTER(LjParams), P, P, P, C.c_uint, SZ, C.c_int, SZ, F3, C.c_int,
                                         C.c_float, P, P, P, SZ, P, C.c_float, P]),
-    "hx_pair_force_set_lanes": (C.c_int, [C.c_int]),
-    "hx_pair_force_set_packed": (C.c_int, [C.c_int]),
+    "hx_shell_rows_plan": (C.c_int, [C.c_float, C.POINTER(ShellRows)]),
+    "hx_count_max": (C.c_int, [P, SZ, P, P]),
+    "hx_shell_rows_build": (C.c_int, [C.POINTER(LjParams), P, SZ, P, P, P, SZ, F3, C.POINTER(ShellRows), P]),
+    "hx_pair_force_shells": (C.c_int, [C.POINTER(LjParams), P, P, C.POINTER(ShellRows), P, SZ, F3, C.c_int, C.c_int, P, P,
+                                       C.c_float, P]),
     "hx_verlet_integrate": (C.c_int, [P, P, P, P, SZ, C.c_float, F3, P]),
     "hx_verlet_finalize": (C.c_int, [P, P, SZ, C.c_float, P]),
     "hx_verlet_finalize_integrate": (C.c_int, [P, P, P, P, SZ, SZ, C.c_float, F3, C.c_int, P, P, P]),
@@ -168,10 +183,13 @@ _module_protos = {
     "hxm_neighbour_stride": (SZ, [P]),
     "hxm_neighbour_layout": (C.c_int, [P]),
     "hxm_neighbour_check": (C.c_int, [P, C.POINTER(C.c_int)]),
+    "hxm_neighbour_set_shell_rows": (C.c_int, [P, C.c_int]),
     "hxm_neighbour_updates": (SZ, [P]),
     "hxm_neighbour_mean_length": (C.c_double, [P]),
     "hxm_neighbour_get": (C.c_int, [P, P, P]),
     "hxm_neighbour_device_ptr": (P, [P]),
+    "hxm_neighbour_named_ptr": (P, [P, C.c_char_p]),
+    "hxm_neighbour_ctl_read": (C.c_int, [P, C.POINTER(C.c_uint32)]),
     "hxm_force_pair_trunc_create": (C.c_int, [P, P, D3, P, C.c_float, PP]),
     "hxm_force_destroy": (None, [P]),
     "hxm_force_apply": (C.c_int, [P]),

@@ -11,11 +11,13 @@
 namespace hx {
 
 // cell index of a position, binning_kernel.cu:34-54:  (uint)(r / l + n) % n, x fastest.
-// IEEE division (the reference's -prec-div=false division differs by <= 2 ulp).
+// The quotient is the reference build's (-prec-div=false, --fmad=true, -ftz=true: cmake/platform.cmake:75), read off
+// the SASS of its compute_cell kernel (oracle/_ref/obj/binning_kernel.o): MUFU.RCP(l), then ONE fused
+// FFMA.FTZ rcp * r + float(n) and a truncating conversion — so a particle within an ulp of a cell face lands in the
+// cell the reference puts it in.
 __device__ __forceinline__ unsigned cell_coord(float r, float len, unsigned n)
 {
-    float t = __fadd_rn(__fdiv_rn(r, len), static_cast<float>(n));
-    return __float2uint_rz(t) % n;
+    return __float2uint_rz(fma_ftz(rcp_approx(len), r, static_cast<float>(n))) % n;
 }
 
 __global__ void k_cell_claim(const float4* __restrict__ pos_hi, unsigned n, vec3 cell_len, uvec3 ncell,
@@ -36,6 +38,13 @@ __global__ void k_cell_claim(const float4* __restrict__ pos_hi, unsigned n, vec3
     if (cell_index) cell_index[i] = c;
     unsigned s = atomicAdd(&cell_count[c], 1u);
     if (s < cell_size) g_cell[static_cast<size_t>(c) * cell_size + s] = i;
+}
+
+// MUFU.RCP of a few host values (see hx_device_rcp)
+__global__ void k_device_rcp(const float* __restrict__ x, float* __restrict__ out, unsigned n)
+{
+    unsigned const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rcp_approx(x[i]);
 }
 
 // one warp per cell: sort the claimed entries ascending (placeholders = 0xFFFFFFFF sort last)
@@ -121,4 +130,29 @@ extern "C" int hx_binning_update(const hx_float4* position_hi_dev, size_t nparti
     k_cell_sort<<<div_up(ncells, warps), warps * 32, warps * pow2 * sizeof(unsigned), st>>>(
         g_cell_dev, cell_count_dev, static_cast<unsigned>(ncells), cell_size, pow2, overflow_flag_dev);
     return check_launch("k_cell_sort");
+}
+
+// The divisions of the path by cell and box lengths are r * MUFU.RCP(l) in the reference build (binning_kernel.cu:34-54,
+// hilbert_kernel.cu:59); this evaluates that hardware reciprocal for host values so that a host-side restatement of
+// the arithmetic (oracle/hx_oracle.c, a host class that wants to predict a cell) can use the device's value.
+extern "C" int hx_device_rcp(const float* x_host, float* rcp_host, unsigned n)
+{
+    if (!x_host || !rcp_host || n == 0 || n > 1024) {
+        hx::set_error("hx_device_rcp: invalid argument");
+        return HX_E_INVALID;
+    }
+    float* d = nullptr;
+    cudaError_t err = cudaMalloc(&d, 2 * n * sizeof(float));
+    if (err == cudaSuccess) err = cudaMemcpy(d, x_host, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) {
+        hx::k_device_rcp<<<(n + 127) / 128, 128>>>(d, d + n, n);
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaMemcpy(rcp_host, d + n, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (d) cudaFree(d);
+    if (err != cudaSuccess) {
+        hx::set_error("hx_device_rcp: %s", cudaGetErrorString(err));
+        return static_cast<int>(err);
+    }
+    return HX_OK;
 }

@@ -162,6 +162,13 @@ struct hxm_neighbour {
     size_t stride = 0;
     uint32_t *g_neighbour = nullptr, *count = nullptr;
     int *flag = nullptr, *h_flag = nullptr;
+    // private shell-ordered copy of the rows for the pair-force kernel (ROW layout only)
+    bool use_shells = true;
+    hx_shell_rows shells = {};
+    size_t shell_words = 0;        // allocated words of shells.rows_dev
+    uint32_t* count_max = nullptr; // device word: longest list of the last build
+    const hx_lj_params* shell_potential = nullptr;   // cutoffs the shells refer to (set by the force module)
+    bool shells_valid = false;
     // max_displacement
     float4* r0 = nullptr;
     uint32_t* ctl = nullptr;       // device control block (4 words), ctl[0] = max rr bits
@@ -181,7 +188,7 @@ struct hxm_neighbour {
     {
         if (own_binning) delete binning;
         dev_free(g_neighbour); dev_free(count); dev_free(flag); dev_free(r0); dev_free(ctl); dev_free(keys);
-        dev_free(index);
+        dev_free(index); dev_free(shells.rows_dev); dev_free(shells.ends_dev); dev_free(count_max);
         if (sort_scratch) cudaFree(sort_scratch);
         if (h_flag) cudaFreeHost(h_flag);
         if (h_ctl) cudaFreeHost(h_ctl);
@@ -231,9 +238,12 @@ struct hxm_neighbour {
             HXM_TRY(hx_nlist_build(binning->g_cell, binning->ncell, binning->cell_size,
                                    reinterpret_cast<hx_float4*>(p->pos), p->n, rr_cut_skin, ntype1, ntype2, Lf,
                                    g_neighbour, size, stride, layout, 0, count, flag, p->st));
-            // one host round-trip per list update for both overflow flags
+            bool const want_shells = use_shells && layout == HX_LAYOUT_ROW && shell_potential;
+            if (want_shells) HXM_TRY(hx_count_max(count, p->n, count_max, p->st));
+            // one host round-trip per list update for both overflow flags (and the longest list)
             HXM_CUDA(cudaMemcpyAsync(&h_flag[0], binning->flag, sizeof(int), cudaMemcpyDeviceToHost, p->st));
             HXM_CUDA(cudaMemcpyAsync(&h_flag[1], flag, sizeof(int), cudaMemcpyDeviceToHost, p->st));
+            if (want_shells) HXM_CUDA(cudaMemcpyAsync(&h_flag[2], count_max, sizeof(int), cudaMemcpyDeviceToHost, p->st));
             HXM_CUDA(cudaStreamSynchronize(p->st));
             if (h_flag[0]) {
                 // binning.cpp:216-219 — overcrowded cells: double the cell size
@@ -248,6 +258,7 @@ struct hxm_neighbour {
             break;
         }
         binning->cache_ver = p->pos_ver;
+        HXM_TRY(build_shells());
         // displacement->zero()
         HXM_TRY(hx_displacement_zero(reinterpret_cast<hx_float4*>(p->pos), reinterpret_cast<hx_float4*>(r0), p->n, p->st));
         HXM_TRY(hx_ctl_reset(ctl, p->st));
@@ -255,6 +266,30 @@ struct hxm_neighbour {
         disp_exceeded = false;
         order_ver_seen = p->order_ver;
         updates++;
+        return 0;
+    }
+
+    // private rows for the pair-force kernel: pitch from the longest list of this build (grow-only allocation)
+    int build_shells()
+    {
+        hxm_particle* p = particle;
+        shells_valid = false;
+        if (!(use_shells && layout == HX_LAYOUT_ROW && shell_potential)) return 0;
+        unsigned const longest = static_cast<unsigned>(h_flag[2]);
+        unsigned const pitch = ((longest + 32u) / 32u) * 32u;
+        if (pitch > 512) return 0;                       // (longer lists are served by the public rows)
+        size_t const words = p->n * static_cast<size_t>(pitch) + 64;
+        if (words > shell_words) {
+            dev_free(shells.rows_dev);
+            HXM_TRY(dev_alloc(&shells.rows_dev, words));
+            shell_words = words;
+        }
+        if (!shells.ends_dev) HXM_TRY(dev_alloc(&shells.ends_dev, p->n * HX_NSHELL));
+        shells.pitch = pitch;
+        HXM_TRY(hx_shell_rows_plan(r_skin, &shells));
+        hx_float4* pos = reinterpret_cast<hx_float4*>(p->pos);
+        HXM_TRY(hx_shell_rows_build(shell_potential, g_neighbour, stride, count, pos, pos, p->n, Lf, &shells, p->st));
+        shells_valid = true;
         return 0;
     }
 
@@ -301,7 +336,13 @@ struct hxm_force {
         hxm_particle* p = particle;
         hx_float4* pos = reinterpret_cast<hx_float4*>(p->pos);
         int const layout = neighbour->layout | (p->reduced ? HX_FORCE_POSITIONS_REDUCED : 0);
-        if (ctl) {
+        if (!aux && neighbour->shells_valid && neighbour->shell_potential == &potential->p) {
+            // shell-ordered private rows: walks only the entries that can lie inside the cutoff
+            HXM_TRY(hx_pair_force_shells(&potential->p, pos, pos, &neighbour->shells,
+                                         reinterpret_cast<hx_float4*>(neighbour->r0), p->n, Lf,
+                                         p->reduced ? HX_FORCE_POSITIONS_REDUCED : 0, 1,
+                                         reinterpret_cast<hx_float4*>(p->force), ctl, skin_half, p->st));
+        } else if (ctl) {
             HXM_TRY(hx_pair_force_guarded(&potential->p, pos, pos, neighbour->g_neighbour, neighbour->size,
                                           neighbour->stride, layout, p->n, Lf, 1, weight(),
                                           reinterpret_cast<hx_float4*>(p->force), aux ? p->en_pot : nullptr,
@@ -1024,7 +1065,8 @@ int hxm_neighbour_create(hxm_particle* particle, const double box_length[3], con
     HXM_TRY(dev_alloc(&nb->index, particle->A));
     nb->sort_scratch_bytes = hx_sort_scratch_bytes(n);
     HXM_CUDA(cudaMalloc(&nb->sort_scratch, nb->sort_scratch_bytes));
-    HXM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&nb->h_flag), 2 * sizeof(int)));
+    HXM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&nb->h_flag), 4 * sizeof(int)));
+    HXM_TRY(dev_alloc(&nb->count_max, 1));
     HXM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&nb->h_ctl), 4 * sizeof(uint32_t)));
     HXM_TRY(hx_ctl_reset(nb->ctl, particle->st));
     nb->depth = hx_hilbert_depth(box_length);
@@ -1040,6 +1082,37 @@ size_t hxm_neighbour_stride(const hxm_neighbour* nb) { return nb->stride; }
 int hxm_neighbour_layout(const hxm_neighbour* nb) { return nb->layout; }
 size_t hxm_neighbour_updates(const hxm_neighbour* nb) { return nb->updates; }
 const void* hxm_neighbour_device_ptr(const hxm_neighbour* nb) { return nb->g_neighbour; }
+
+const void* hxm_neighbour_named_ptr(const hxm_neighbour* nb, const char* name_c)
+{
+    std::string name(name_c ? name_c : "");
+    if (!nb) return nullptr;
+    if (name == "g_neighbour") return nb->g_neighbour;
+    if (name == "count") return nb->count;
+    if (name == "r0") return nb->r0;
+    if (name == "ctl") return nb->ctl;
+    if (name == "shell_rows") return nb->shells_valid ? &nb->shells : nullptr;      // host pointer to the descriptor
+    set_error("neighbour: unknown array '%s'", name_c ? name_c : "(null)");
+    return nullptr;
+}
+
+int hxm_neighbour_ctl_read(hxm_neighbour* nb, uint32_t ctl_out[4])
+{
+    if (!nb || !ctl_out) return HX_E_INVALID;
+    HXM_CUDA(cudaMemcpyAsync(nb->h_ctl, nb->ctl, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, nb->particle->st));
+    HXM_CUDA(cudaStreamSynchronize(nb->particle->st));
+    for (int k = 0; k < 4; ++k) ctl_out[k] = nb->h_ctl[k];
+    return 0;
+}
+
+int hxm_neighbour_set_shell_rows(hxm_neighbour* nb, int enable)
+{
+    if (!nb) return HX_E_INVALID;
+    nb->use_shells = enable != 0;
+    if (!nb->use_shells) nb->shells_valid = false;
+    else if (nb->updates > 0) nb->order_ver_seen = 0;      // rebuilt (with the private rows) at the next check
+    return 0;
+}
 
 int hxm_neighbour_check(hxm_neighbour* nb, int* rebuilt)
 {
@@ -1092,6 +1165,8 @@ int hxm_force_pair_trunc_create(hxm_potential* potential, hxm_particle* particle
     f->neighbour = neighbour;
     f->aux_weight = aux_weight;
     for (int d = 0; d < 3; ++d) f->Lf[d] = static_cast<float>(box_length[d]);
+    // the first pair force bound to the lists decides the cutoffs of their private shell rows
+    if (!neighbour->shell_potential && !potential->p.hard_core) neighbour->shell_potential = &potential->p;
     *out = f.release();
     return 0;
 }

@@ -9,6 +9,7 @@
 // time, tests 32 candidates per step and compacts the accepted ones with ballot/popc, which preserves
 // the reference's list order exactly.  Row layout writes are fully coalesced.
 #include "common.cuh"
+#include <algorithm>
 
 namespace hx {
 
@@ -258,6 +259,113 @@ __global__ void __launch_bounds__(NL_THREADS) k_nlist_build(nlist_args a)
     }
 }
 
+// ---- private rows ordered by shells of the build-time distance (see force.cu, k_force_shell) -----------------------
+struct shell_build_args {
+    const unsigned* nl;
+    const unsigned* count;
+    const float4* pos1;
+    const float4* pos2;
+    unsigned* rows;
+    uint4* ends;
+    size_t stride;
+    unsigned n, pitch, ntype2;
+    vec3 L, invL;
+    float t2[HX_MAX_PAIR_TYPES][HX_NSHELL - 1];     // (r_cut_ab + delta[s])^2
+};
+
+constexpr unsigned SB_WARPS = 8;
+constexpr unsigned SB_MAX = 512;                     // longest list served (entries)
+constexpr unsigned SB_SLOTS = SB_MAX / 32;
+
+// One warp per particle.  Pass 1 classifies every entry of the public row (gather, distance as in the list build,
+// thresholds) and counts, per slot of 32 entries and shell, with match.any; an exclusive scan over (shell, slot)
+// then gives every entry its place: shells in ascending order, entries of a shell in the order of the public row,
+// so the result is deterministic.
+__global__ void __launch_bounds__(SB_WARPS * 32) k_shell_rows(shell_build_args a)
+{
+    __shared__ unsigned s_j[SB_WARPS][SB_MAX];
+    __shared__ unsigned char s_sr[SB_WARPS][SB_MAX];          // shell | rank within (slot, shell) << 3
+    __shared__ unsigned s_cnt[SB_WARPS][HX_NSHELL * SB_SLOTS];   // [shell][slot]
+    unsigned const lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    unsigned const i = blockIdx.x * SB_WARPS + w;
+    if (i >= a.n) return;
+    unsigned const lane_lt = (1u << lane) - 1u;
+    unsigned const cnt = min(a.count[i], SB_MAX);
+    unsigned const nslot = (cnt + 31u) / 32u;
+    float4 const r1 = a.pos1[i];
+    const float* const t2 = a.t2[__float_as_uint(r1.w) * a.ntype2];
+    const unsigned* const src = a.nl + static_cast<size_t>(i) * a.stride;
+#pragma unroll
+    for (unsigned c = lane; c < HX_NSHELL * SB_SLOTS; c += 32) s_cnt[w][c] = 0;
+    __syncwarp();
+    for (unsigned slot = 0; slot < nslot; ++slot) {
+        unsigned const k = slot * 32 + lane;
+        bool const valid = k < cnt;
+        unsigned const j = valid ? src[k] : i;
+        float4 const r2 = a.pos2[j];
+        float const dx = minimg(__fsub_rn(r1.x, r2.x), a.L.x, a.invL.x);
+        float const dy = minimg(__fsub_rn(r1.y, r2.y), a.L.y, a.invL.y);
+        float const dz = minimg(__fsub_rn(r1.z, r2.z), a.L.z, a.invL.z);
+        float const rr = norm2(dx, dy, dz);
+        const float* const th = t2 + (HX_NSHELL - 1) * __float_as_uint(r2.w);
+        unsigned sh = 0;
+#pragma unroll
+        for (int q = 0; q < HX_NSHELL - 1; ++q) sh += rr > th[q] ? 1u : 0u;
+        if (!valid) sh = HX_NSHELL;                             // (a group of its own, not counted)
+        unsigned const m = __match_any_sync(0xFFFFFFFFu, sh);
+        unsigned const rank = __popc(m & lane_lt);
+        if (valid) {
+            if (rank == 0) s_cnt[w][sh * SB_SLOTS + slot] = __popc(m);
+            s_j[w][k] = j;
+            s_sr[w][k] = static_cast<unsigned char>(sh | (rank << 3));
+        }
+    }
+    __syncwarp();
+    // exclusive scan over the HX_NSHELL * SB_SLOTS = 128 cells in (shell, slot) order: 4 consecutive cells per lane
+    unsigned c[4], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { c[q] = s_cnt[w][4 * lane + q]; sum += c[q]; }
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned const t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= static_cast<unsigned>(o)) incl += t;
+    }
+    unsigned base = incl - sum;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { s_cnt[w][4 * lane + q] = base; base += c[q]; }
+    // end of shell s = inclusive sum through its last cell (lane 4 s + 3 holds cells of shell s only: SB_SLOTS == 16)
+    static_assert(SB_SLOTS == 16 && HX_NSHELL == 8, "scan layout");
+    unsigned e[HX_NSHELL];
+#pragma unroll
+    for (int sidx = 0; sidx < HX_NSHELL; ++sidx) e[sidx] = __shfl_sync(0xFFFFFFFFu, incl, 4 * sidx + 3);
+    __syncwarp();
+    unsigned* const dst = a.rows + static_cast<size_t>(i) * a.pitch;
+    for (unsigned slot = 0; slot < nslot; ++slot) {
+        unsigned const k = slot * 32 + lane;
+        if (k < cnt) {
+            unsigned const sr = s_sr[w][k];
+            unsigned const sh = sr & 7u, rank = sr >> 3;
+            dst[s_cnt[w][sh * SB_SLOTS + slot] + rank] = s_j[w][k];
+        }
+    }
+    // the rest of the row holds the particle's own index: safe to gather, masked by its position
+    for (unsigned k = cnt + lane; k < a.pitch; k += 32) dst[k] = i;
+    if (lane == 0)
+        a.ends[i] = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+    // slack behind the last row (read ahead by the force kernel, never used)
+    if (i == a.n - 1)
+        for (unsigned k = lane; k < 64; k += 32) a.rows[static_cast<size_t>(a.n) * a.pitch + k] = 0;
+}
+
+__global__ void k_count_max(const unsigned* __restrict__ count, unsigned n, unsigned* __restrict__ out)
+{
+    unsigned m = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, count[i]);
+    m = __reduce_max_sync(0xFFFFFFFFu, m);
+    if ((threadIdx.x & 31u) == 0 && m > 0) atomicMax(out, m);
+}
+
 } // namespace hx
 
 using namespace hx;
@@ -361,4 +469,67 @@ extern "C" int hx_nlist_build2(const uint32_t* g_cell_dev, const unsigned ncell[
 {
     return nlist_build_impl(g_cell_dev, ncell, cell_size, position_hi_dev, nparticle, nbuild, rr_cut_skin, ntype1, ntype2,
                             box_length, g_neighbour_dev, size, stride, layout, fill_all, count_dev, overflow_flag_dev, stream);
+}
+
+extern "C" int hx_shell_rows_plan(float skin, hx_shell_rows* shells)
+{
+    if (!shells || !(skin > 0)) {
+        set_error("hx_shell_rows_plan: invalid argument");
+        return HX_E_INVALID;
+    }
+    for (int s = 0; s < HX_NSHELL; ++s) shells->delta[s] = skin * static_cast<float>(s + 1) / HX_NSHELL;
+    return HX_OK;
+}
+
+extern "C" int hx_count_max(const uint32_t* count_dev, size_t n, uint32_t* max_dev, void* stream)
+{
+    if (!count_dev || !max_dev || n >= 0xFFFFFFFFull) {
+        set_error("hx_count_max: invalid argument");
+        return HX_E_INVALID;
+    }
+    cudaStream_t st = as_stream(stream);
+    cudaError_t err = cudaMemsetAsync(max_dev, 0, sizeof(uint32_t), st);
+    if (err != cudaSuccess) {
+        set_error("hx_count_max: memset: %s", cudaGetErrorString(err));
+        return static_cast<int>(err);
+    }
+    if (n == 0) return HX_OK;
+    unsigned const blocks = static_cast<unsigned>(std::min<size_t>((n + 1023) / 1024, 592));
+    k_count_max<<<blocks, 256, 0, st>>>(count_dev, static_cast<unsigned>(n), max_dev);
+    return check_launch("k_count_max");
+}
+
+extern "C" int hx_shell_rows_build(const hx_lj_params* potential, const uint32_t* g_neighbour_dev, size_t stride,
+                                   const uint32_t* count_dev, const hx_float4* position1_hi_dev,
+                                   const hx_float4* position2_hi_dev, size_t nparticle, const float box_length[3],
+                                   const hx_shell_rows* shells, void* stream)
+{
+    if (!potential || !g_neighbour_dev || !count_dev || !position1_hi_dev || !position2_hi_dev || !box_length || !shells
+        || !shells->rows_dev || !shells->ends_dev || shells->pitch < 32 || shells->pitch % 32 != 0 || shells->pitch > SB_MAX
+        || nparticle >= 0x7FFFFFFFull || potential->ntype1 * potential->ntype2 == 0
+        || potential->ntype1 * potential->ntype2 > HX_MAX_PAIR_TYPES) {
+        set_error("hx_shell_rows_build: invalid argument");
+        return HX_E_INVALID;
+    }
+    if (nparticle == 0) return HX_OK;
+    shell_build_args a;
+    a.nl = g_neighbour_dev;
+    a.count = count_dev;
+    a.pos1 = reinterpret_cast<const float4*>(position1_hi_dev);
+    a.pos2 = reinterpret_cast<const float4*>(position2_hi_dev);
+    a.rows = shells->rows_dev;
+    a.ends = reinterpret_cast<uint4*>(shells->ends_dev);
+    a.stride = stride;
+    a.n = static_cast<unsigned>(nparticle);
+    a.pitch = shells->pitch;
+    a.ntype2 = potential->ntype2;
+    a.L = make_vec3(box_length);
+    a.invL = {1.0f / box_length[0], 1.0f / box_length[1], 1.0f / box_length[2]};
+    for (unsigned t = 0; t < HX_MAX_PAIR_TYPES; ++t)
+        for (int s = 0; s < HX_NSHELL - 1; ++s) {
+            float const r = (t < potential->ntype1 * potential->ntype2 ? potential->r_cut[t] : 0.f) + shells->delta[s];
+            a.t2[t][s] = r * r;
+        }
+    k_shell_rows<<<div_up(nparticle, SB_WARPS), SB_WARPS * 32, 0, as_stream(stream)>>>(a);
+    return check_launch("k_shell_rows");
 }

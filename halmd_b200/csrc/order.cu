@@ -13,11 +13,14 @@ namespace hx {
 // octant sequence is the binary expansion of the integer lattice coordinate (MSB first, a set bit
 // meaning the non-negative half); the coordinate n (r/L - floor(r/L) rounding up to 1) behaves as n-1.
 // The vertex/orientation update (Wang & Shan 2005) is kept table driven.
+// The float arithmetic that decides the lattice cell is the reference build's, read off the SASS of its map kernel
+// (oracle/_ref/obj/hilbert_kernel.o; -prec-div=false -ftz=true): element_div(r, L) is r * MUFU.RCP(L) (FMUL.FTZ, not
+// fused), then t - floor(t) and the product with float(n), each rounded separately.
 __device__ __forceinline__ unsigned lattice_coord(float r, float L, unsigned n)
 {
-    float t = __fdiv_rn(r, L);
-    float f = __fsub_rn(t, floorf(t));
-    unsigned c = __float2uint_rz(floorf(__fmul_rn(f, static_cast<float>(n))));
+    float const t = mul_ftz(rcp_approx(L), r);
+    float const f = sub_ftz(t, floor_ftz(t));
+    unsigned const c = __float2uint_rz(floor_ftz(mul_ftz(static_cast<float>(n), f)));
     return min(c, n - 1);
 }
 

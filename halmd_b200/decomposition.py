@@ -200,10 +200,14 @@ class DecomposedSystem:
         self.updates = 0
         self.sorting = sorting
         self.stats = {"chunks": 0, "syncs": 0, "migrated": 0}
-        hx.check(self.lib.hx_pair_force_set_lanes(lanes))
+        self.lanes_flag = hx.FORCE_LANES(lanes)
 
         nt = int(nspecies)
-        trunc = {"sharp": hx.TRUNC_SHARP, "shifted": hx.TRUNC_SHIFTED, "smooth_r4": hx.TRUNC_SMOOTH_R4}[truncation]
+        trunc_map = {"sharp": hx.TRUNC_SHARP, "shifted": hx.TRUNC_SHIFTED, "smooth_r4": hx.TRUNC_SMOOTH_R4,
+                     "force_shifted": hx.TRUNC_FORCE_SHIFTED}
+        if truncation not in trunc_map:
+            raise hx.HxError(f"unknown truncation '{truncation}'")
+        trunc = trunc_map[truncation]
         self.pot = hx.LjParams()
         hx.check(self.lib.hx_potential_lj_init(C.byref(self.pot), nt, nt, hx.farr(epsilon), hx.farr(sigma), trunc,
                                                hx.farr(cutoff), float(h)), "potential")
@@ -489,7 +493,7 @@ class DecomposedSystem:
     def _force(self, aux=False, guarded=False):
         hx = self.hx
         hx.check(self.lib.hx_pair_force2(C.byref(self.pot), self._p(self.pos), self._p(self.pos), self.n_own + self.n_ghost,
-                                         self._p(self.nl), self.size, self.stride, hx.LAYOUT_ROW, self.n_own, self.Lf, 1, 0.5,
+                                         self._p(self.nl), self.size, self.stride, hx.LAYOUT_ROW | self.lanes_flag, self.n_own, self.Lf, 1, 0.5,
                                          self._p(self.force), self._p(self.en_pot) if aux else None,
                                          self._p(self.stress) if aux else None, self.cap,
                                          self._p(self.ctl) if guarded else None, self.skin_half, self.st), "pair_force")

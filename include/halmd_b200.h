@@ -49,6 +49,11 @@ extern "C" {
  * (verlet_kernel.cu:60-62, box_kernel.cuh:37-45).  Particles farther than r_cut from all faces then skip the
  * minimum-image arithmetic (same results: their pairs within the cutoff have image 0). */
 #define HX_FORCE_POSITIONS_REDUCED 0x100
+/* further per-call bits of `layout` for the ROW layout (tuning; defaults = packed f32x2 arithmetic, 4 lanes):
+ * HX_FORCE_SCALAR selects the scalar instruction stream, HX_FORCE_LANES(l) l = 2, 4 or 8 lanes cooperating on one
+ * particle (the reference's unroll_force_loop variant uses a whole warp, pair_trunc_kernel.cuh:54-154) */
+#define HX_FORCE_SCALAR 0x200
+#define HX_FORCE_LANES(l) ((l) << 12)
 
 /* potential truncations (halmd/mdsim/gpu/potentials/pair/truncations/) */
 #define HX_TRUNC_SHARP     0
@@ -88,6 +93,11 @@ int hx_binning_update(const hx_float4* position_hi_dev, size_t nparticle,
                       const float cell_length[3], const unsigned ncell[3], unsigned cell_size,
                       uint32_t* g_cell_dev, uint32_t* cell_count_dev, uint32_t* cell_index_dev,
                       int* overflow_flag_dev, void* stream);
+
+/* MUFU.RCP (rcp.approx.ftz.f32) of n <= 1024 host values, synchronously: the reference build (-prec-div=false) divides
+ * by cell and box lengths as r * MUFU.RCP(l) (binning_kernel.cu:34-54, hilbert_kernel.cu:59), and so do the kernels
+ * here; a host-side restatement of that arithmetic needs the device's reciprocal of those few constants. */
+int hx_device_rcp(const float* x_host, float* rcp_host, unsigned n);
 
 /* ---- a4: Hilbert space-filling-curve order ---------------------------------------------
  * halmd/mdsim/gpu/sorts/hilbert.cpp:51-54 (depth), :71-117; hilbert_kernel.cu:38-69;
@@ -182,10 +192,39 @@ int hx_pair_force(const hx_lj_params* potential, const hx_float4* position1_hi_d
                   const float box_length[3], int force_zero, float aux_weight,
                   hx_float4* force_dev, float* en_pot_dev, float* stress_dev,
                   size_t stress_stride, void* stream);
-/* tuning knob for the ROW layout: lanes cooperating on one particle (2, 4 or 8) */
-int hx_pair_force_set_lanes(int lanes);
-/* tuning knob: packed f32x2 arithmetic in the ROW kernel (default 1); 0 selects the scalar instruction stream */
-int hx_pair_force_set_packed(int enable);
+
+/* ---- a8, private list format: rows ordered by shells of the pair distance at build time ---------------------------
+ * The reference walks every stored neighbour and discards those outside r_cut (pair_trunc_kernel.cuh:205-224: 94.5
+ * stored, 55.3 inside at config 2).  hx_shell_rows_build copies a ROW-layout list (which stays untouched and
+ * bit-identical to the reference's) into private rows in which the entries of a particle are grouped by
+ * r_build - r_cut_ab in (delta[s-1], delta[s]] (stable within a shell), records the end of every shell per particle,
+ * and fills the rest of each row with the particle's own index.  hx_pair_force_shells walks, for particle i, only the
+ * shells with delta[s-1] < |r_i - r0_i| + sqrt(ctl[0]) (+ rounding margin): by the triangle inequality no other entry can
+ * lie inside the cutoff, so forces equal those of hx_pair_force up to the order of the compensated summation.
+ * r0_dev (positions at the list build) and ctl_dev (ctl[0] = running maximum squared displacement of ALL particles
+ * whose indices appear in the rows, ghosts included) may be NULL: the whole row is walked then.  ctl_dev also guards
+ * the launch as in hx_pair_force_guarded.  No aux variables (use hx_pair_force for en_pot / stress) and no hard_core.
+ * rows_dev: nparticle * pitch + 64 words (the slack must hold valid indices, e.g. zeros; build writes it);
+ * ends_dev: nparticle * HX_NSHELL uint16, 16-byte aligned; pitch: multiple of 32, > longest list. */
+#define HX_NSHELL 8
+typedef struct hx_shell_rows {
+    uint32_t* rows_dev;
+    uint16_t* ends_dev;
+    unsigned pitch;
+    float delta[HX_NSHELL];   /* ascending, delta[HX_NSHELL-1] >= skin */
+} hx_shell_rows;
+/* delta[s] = skin * (s + 1) / HX_NSHELL */
+int hx_shell_rows_plan(float skin, hx_shell_rows* shells);
+/* largest entry of count_dev[0..n) into *max_dev (the caller picks the pitch from it) */
+int hx_count_max(const uint32_t* count_dev, size_t n, uint32_t* max_dev, void* stream);
+int hx_shell_rows_build(const hx_lj_params* potential, const uint32_t* g_neighbour_dev, size_t stride,
+                        const uint32_t* count_dev, const hx_float4* position1_hi_dev,
+                        const hx_float4* position2_hi_dev, size_t nparticle, const float box_length[3],
+                        const hx_shell_rows* shells, void* stream);
+int hx_pair_force_shells(const hx_lj_params* potential, const hx_float4* position1_hi_dev,
+                         const hx_float4* position2_hi_dev, const hx_shell_rows* shells, const hx_float4* r0_dev,
+                         size_t nparticle, const float box_length[3], int flags /* HX_FORCE_* bits */, int force_zero,
+                         hx_float4* force_dev, uint32_t* ctl_dev, float skin_half, void* stream);
 
 /* ---- f1: external one-body force, planar Lennard-Jones 9-3 walls -----------------------------------------------
  * halmd/mdsim/gpu/forces/external.hpp:120-190, external_kernel.cuh:49-103,

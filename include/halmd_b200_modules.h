@@ -97,12 +97,21 @@ int hxm_neighbour_layout(const hxm_neighbour* nb);
 /* neighbour:g_neighbour() semantics: rebuild iff positions moved > skin/2 or particles were reordered; returns 1 in
  * *rebuilt when an update ran */
 int hxm_neighbour_check(hxm_neighbour* nb, int* rebuilt);
+/* private shell-ordered rows for the pair-force kernel (halmd_b200.h, hx_shell_rows_build; default on for the ROW
+ * layout): enable = 0 makes the force module walk the public lists; a change takes effect with the next list update */
+int hxm_neighbour_set_shell_rows(hxm_neighbour* nb, int enable);
 /* statistics: number of list updates so far; mean list length of the last update */
 size_t hxm_neighbour_updates(const hxm_neighbour* nb);
 double hxm_neighbour_mean_length(hxm_neighbour* nb);
 /* copy lists to host (size*stride or n*stride uint32) and per-particle counts (n uint32); either may be NULL */
 int hxm_neighbour_get(hxm_neighbour* nb, uint32_t* list_host, uint32_t* count_host);
 const void* hxm_neighbour_device_ptr(const hxm_neighbour* nb);
+/* further arrays of the module: "g_neighbour", "count" (uint32[n]), "r0" (float4[n], positions at the last update),
+ * "ctl" (the 4-word control block of halmd_b200.h) as device pointers; "shell_rows" as a HOST pointer to the
+ * hx_shell_rows descriptor of the private rows (NULL while they are not in use) */
+const void* hxm_neighbour_named_ptr(const hxm_neighbour* nb, const char* name);
+/* synchronising read of the control block (ctl[0] = float bits of the largest squared displacement since the last update) */
+int hxm_neighbour_ctl_read(hxm_neighbour* nb, uint32_t ctl_out[4]);
 
 /* ---- mdsim.forces.pair (pair_trunc) ------------------------------------------------------------------------------- */
 int hxm_force_pair_trunc_create(hxm_potential* potential, hxm_particle* particle, const double box_length[3],

@@ -148,13 +148,55 @@ unsigned oracle_hilbert_depth(const double L[3])
     return depth < 10 ? depth : 10;
 }
 
+/* ---- the reference build's division by a constant --------------------------------------------------------------
+ * Under -prec-div=false (cmake/platform.cmake:75) r / l is r * MUFU.RCP(l).  MUFU.RCP is a hardware approximation
+ * (<= 1 ulp) that cannot be restated on a CPU, but the divisors on this path are a handful of constants (cell
+ * lengths, box lengths): GPU tests install a callback that evaluates MUFU.RCP for them on the device (the product's
+ * hx_device_rcp); the values are cached here and everything else is restated in C.  Without a callback (CPU-only
+ * tests) the IEEE reciprocal stands in, which moves only particles within an ulp of a cell face / lattice plane. */
+static struct { float x, rcp; } rcp_table[64];
+static unsigned rcp_count = 0;
+typedef float (*oracle_rcp_fn)(float);
+static oracle_rcp_fn rcp_fn = NULL;
+
+void oracle_set_device_rcp_fn(oracle_rcp_fn fn)
+{
+    rcp_fn = fn;
+    rcp_count = 0;
+}
+
+void oracle_set_device_rcp(const float* x, const float* rcp, unsigned count)
+{
+    for (unsigned k = 0; k < count; ++k) {
+        unsigned slot = rcp_count < 64 ? rcp_count : 0;
+        for (unsigned q = 0; q < rcp_count; ++q)
+            if (fbits(rcp_table[q].x) == fbits(x[k])) slot = q;
+        rcp_table[slot].x = x[k];
+        rcp_table[slot].rcp = rcp[k];
+        if (slot == rcp_count) rcp_count++;
+    }
+}
+
+static inline float device_rcp(float x)
+{
+    for (unsigned q = 0; q < rcp_count; ++q)
+        if (fbits(rcp_table[q].x) == fbits(x)) return rcp_table[q].rcp;
+    if (rcp_fn) {
+        float r = rcp_fn(x);
+        oracle_set_device_rcp(&x, &r, 1);
+        return r;
+    }
+    return 1.0f / x;
+}
+
 /* ---- binning: halmd/mdsim/gpu/binning_kernel.cu:34-139, binning.cpp:166-221 ---------------------------
- * cell = (uint)(r / l + n) % n per dimension (IEEE division in place of the approximate one), x fastest. */
+ * cell = (uint)(r / l + n) % n per dimension, x fastest; as compiled: ONE fused multiply-add rcp(l) * r + n
+ * (--fmad=true), then the truncating conversion. */
 static inline uint32_t cell_index(f4 p, const float cl[3], const unsigned nc[3])
 {
-    uint32_t ix = f2u_rz(p.x / cl[0] + (float)nc[0]) % nc[0];
-    uint32_t iy = f2u_rz(p.y / cl[1] + (float)nc[1]) % nc[1];
-    uint32_t iz = f2u_rz(p.z / cl[2] + (float)nc[2]) % nc[2];
+    uint32_t ix = f2u_rz(fmaf(device_rcp(cl[0]), p.x, (float)nc[0])) % nc[0];
+    uint32_t iy = f2u_rz(fmaf(device_rcp(cl[1]), p.y, (float)nc[1])) % nc[1];
+    uint32_t iz = f2u_rz(fmaf(device_rcp(cl[2]), p.z, (float)nc[2])) % nc[2];
     return (iz * nc[1] + iy) * nc[0] + ix;
 }
 
@@ -228,8 +270,8 @@ void oracle_hilbert_keys(const f4* pos, size_t nslots, const float L[3], unsigne
 {
     for (size_t i = 0; i < nslots; ++i) {
         if (fbits(pos[i].w) == PH) { keys[i] = PH; continue; }
-        /* r = element_div(r, box_length): IEEE division in place of the approximate one */
-        keys[i] = hilbert_map(pos[i].x / L[0], pos[i].y / L[1], pos[i].z / L[2], depth);
+        /* r = element_div(r, box_length): r * rcp(L) as compiled (-prec-div=false), one rounding */
+        keys[i] = hilbert_map(pos[i].x * device_rcp(L[0]), pos[i].y * device_rcp(L[1]), pos[i].z * device_rcp(L[2]), depth);
     }
 }
 

@@ -54,8 +54,7 @@ for layout in (0, 1):
     out[f"force_reference_{key}_ms"] = min(t[1:])
     par = tr.lj_params(hx, 1, [1.0], [1.0], 2, [2.5], 0.005, None)
     d_f = dev.zeros((A, 4), np.float32)
-    hx.check(hx.lib.hx_pair_force_set_lanes(4 if layout else 8))
-    flags = hx.FORCE_POSITIONS_REDUCED
+    flags = hx.FORCE_POSITIONS_REDUCED | hx.FORCE_LANES(4 if layout else 8)
     out[f"force_product_{key}_ms"] = ours(lambda: hx.check(hx.lib.hx_pair_force(
         C.byref(par), dev.p(s["d_pos"]), dev.p(s["d_pos"]), dev.p(s["d_nl"]), size, stride, layout | flags, n, hx.f3(s["L"]), 1,
         0.5, dev.p(d_f), None, None, A, dev.stream)))

@@ -35,9 +35,11 @@ def hx():
 
 
 @pytest.fixture(scope="session")
-def cuda():
+def cuda(hx, oracle):
     import torch
     if not torch.cuda.is_available():
         pytest.fail("gpu-marked test started without a CUDA device")
     torch.cuda.set_device(0)
+    import support
+    support.install_device_rcp(hx, oracle)
     return torch

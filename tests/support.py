@@ -203,6 +203,22 @@ def fcc_positions(n, L):
     return r
 
 
+_RCP_FN = C.CFUNCTYPE(C.c_float, C.c_float)
+_rcp_callbacks = []
+
+
+def install_device_rcp(hx, oracle):
+    """GPU runs: the oracle's restatement of the reference build's approximate division (r * MUFU.RCP(l) for cell and
+    box lengths) asks the device for the hardware reciprocal of those constants through the product's hx_device_rcp."""
+    def rcp(x):
+        xin, out = (C.c_float * 1)(x), (C.c_float * 1)()
+        hx.check(hx.lib.hx_device_rcp(xin, out, 1), "hx_device_rcp")
+        return out[0]
+    cb = _RCP_FN(rcp)
+    _rcp_callbacks.append(cb)          # keep the trampoline alive
+    oracle.oracle_set_device_rcp_fn(cb)
+
+
 def melt_like_positions(n, L, rng, jitter=0.12):
     """fcc lattice + Gaussian displacement, wrapped into (-L/2, L/2): a cheap stand-in for a melted fluid with
     no overlapping particles (used where the test does not integrate)."""

@@ -128,6 +128,6 @@ def test_contract_violations_return_error_codes(hx):
     assert hx.lib.hx_potential_lj_init(C.byref(p), 5, 5, hx.farr([1] * 25), hx.farr([1] * 25), 2, hx.farr([2.5] * 25), 0.005) < 0
     assert b"ntype" in hx.lib.hx_last_error_string()
     assert hx.lib.hx_potential_lj_init(C.byref(p), 1, 1, hx.farr([1]), hx.farr([1]), 7, hx.farr([2.5]), 0.005) < 0
-    assert hx.lib.hx_pair_force_set_lanes(3) < 0
+    assert hx.lib.hx_shell_rows_plan(-1.0, None) < 0
     assert hx.lib.hx_displacement_exceeds(np.float32(0.0626).view(np.uint32).item(), 0.5) == 1   # sqrt(.0626) > .25
     assert hx.lib.hx_displacement_exceeds(np.float32(0.0624).view(np.uint32).item(), 0.5) == 0

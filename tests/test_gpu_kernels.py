@@ -303,9 +303,8 @@ def run_force(hx, oracle, dev, s, trunc, aux, eps, sigma, cut, h=0.005, force_ze
         e0[:n] = rng.normal(size=n)
         s0[:] = rng.normal(size=6 * A)
     d_f, d_e, d_s = dev.up(f0), dev.up(e0), dev.up(s0)
-    hx.check(hx.lib.hx_pair_force_set_lanes(lanes))
     hx.check(hx.lib.hx_pair_force(C.byref(par), dev.p(s["d_pos"]), dev.p(s["d_pos"]), dev.p(s["d_nl"]), s["size"],
-                                  s["stride"], s["layout"] | flags, n, hx.f3(s["L"]), force_zero, 0.5,
+                                  s["stride"], s["layout"] | flags | hx.FORCE_LANES(lanes), n, hx.f3(s["L"]), force_zero, 0.5,
                                   dev.p(d_f), dev.p(d_e) if aux else None, dev.p(d_s) if aux else None, A, dev.stream),
              "hx_pair_force")
     of, oe, os_ = f0.copy(), e0.copy(), s0.copy()
