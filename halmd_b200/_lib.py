@@ -112,6 +112,7 @@ _protos = {
     "hx_pair_force_guarded": (C.c_int, [C.POINTER(LjParams), P, P, P, C.c_uint, SZ, C.c_int, SZ, F3, C.c_int,
                                         C.c_float, P, P, P, SZ, P, C.c_float, P]),
     "hx_shell_rows_plan": (C.c_int, [C.c_float, C.POINTER(ShellRows)]),
+    "hx_shell_rows_words": (SZ, [SZ, C.c_uint]),
     "hx_count_max": (C.c_int, [P, SZ, P, P]),
     "hx_shell_rows_build": (C.c_int, [C.POINTER(LjParams), P, SZ, P, P, P, SZ, F3, C.POINTER(ShellRows), P]),
     "hx_pair_force_shells": (C.c_int, [C.POINTER(LjParams), P, P, C.POINTER(ShellRows), P, SZ, F3, C.c_int, C.c_int, P, P,

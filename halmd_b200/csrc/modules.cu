@@ -278,7 +278,7 @@ struct hxm_neighbour {
         unsigned const longest = static_cast<unsigned>(h_flag[2]);
         unsigned const pitch = ((longest + 32u) / 32u) * 32u;
         if (pitch > 512) return 0;                       // (longer lists are served by the public rows)
-        size_t const words = p->n * static_cast<size_t>(pitch) + 64;
+        size_t const words = hx_shell_rows_words(p->n, pitch);
         if (words > shell_words) {
             dev_free(shells.rows_dev);
             HXM_TRY(dev_alloc(&shells.rows_dev, words));

@@ -340,22 +340,26 @@ __global__ void __launch_bounds__(SB_WARPS * 32) k_shell_rows(shell_build_args a
 #pragma unroll
     for (int sidx = 0; sidx < HX_NSHELL; ++sidx) e[sidx] = __shfl_sync(0xFFFFFFFFu, incl, 4 * sidx + 3);
     __syncwarp();
-    unsigned* const dst = a.rows + static_cast<size_t>(i) * a.pitch;
+    unsigned* const dst = a.rows + shell_row_base(i, a.pitch);
     for (unsigned slot = 0; slot < nslot; ++slot) {
         unsigned const k = slot * 32 + lane;
         if (k < cnt) {
             unsigned const sr = s_sr[w][k];
             unsigned const sh = sr & 7u, rank = sr >> 3;
-            dst[s_cnt[w][sh * SB_SLOTS + slot] + rank] = s_j[w][k];
+            dst[shell_row_offset(s_cnt[w][sh * SB_SLOTS + slot] + rank)] = s_j[w][k];
         }
     }
     // the rest of the row holds the particle's own index: safe to gather, masked by its position
-    for (unsigned k = cnt + lane; k < a.pitch; k += 32) dst[k] = i;
+    for (unsigned k = cnt + lane; k < a.pitch; k += 32) dst[shell_row_offset(k)] = i;
     if (lane == 0)
         a.ends[i] = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
-    // slack behind the last row (read ahead by the force kernel, never used)
-    if (i == a.n - 1)
-        for (unsigned k = lane; k < 64; k += 32) a.rows[static_cast<size_t>(a.n) * a.pitch + k] = 0;
+    // rows of a last, incomplete tile and the slack behind it (read ahead by the force kernel, never used)
+    if (i == a.n - 1) {
+        size_t const end = static_cast<size_t>((a.n + 7u) / 8u) * 8u * a.pitch;
+        for (unsigned g = (a.n & 7u) ? (a.n & 7u) : 8u; g < 8u; ++g)
+            for (unsigned k = lane; k < a.pitch; k += 32) a.rows[shell_row_base(a.n - (a.n & 7u) + g, a.pitch) + shell_row_offset(k)] = 0;
+        for (unsigned k = lane; k < HX_SHELL_ROWS_SLACK; k += 32) a.rows[end + k] = 0;
+    }
 }
 
 __global__ void k_count_max(const unsigned* __restrict__ count, unsigned n, unsigned* __restrict__ out)
@@ -479,6 +483,11 @@ extern "C" int hx_shell_rows_plan(float skin, hx_shell_rows* shells)
     }
     for (int s = 0; s < HX_NSHELL; ++s) shells->delta[s] = skin * static_cast<float>(s + 1) / HX_NSHELL;
     return HX_OK;
+}
+
+extern "C" size_t hx_shell_rows_words(size_t nparticle, unsigned pitch)
+{
+    return (nparticle + 7) / 8 * 8 * pitch + HX_SHELL_ROWS_SLACK;
 }
 
 extern "C" int hx_count_max(const uint32_t* count_dev, size_t n, uint32_t* max_dev, void* stream)

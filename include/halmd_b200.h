@@ -204,8 +204,12 @@ int hx_pair_force(const hx_lj_params* potential, const hx_float4* position1_hi_d
  * r0_dev (positions at the list build) and ctl_dev (ctl[0] = running maximum squared displacement of ALL particles
  * whose indices appear in the rows, ghosts included) may be NULL: the whole row is walked then.  ctl_dev also guards
  * the launch as in hx_pair_force_guarded.  No aux variables (use hx_pair_force for en_pot / stress) and no hard_core.
- * rows_dev: nparticle * pitch + 64 words (the slack must hold valid indices, e.g. zeros; build writes it);
- * ends_dev: nparticle * HX_NSHELL uint16, 16-byte aligned; pitch: multiple of 32, > longest list. */
+ * Layout of rows_dev: tiles of 8 consecutive particles (the particles of one warp, 4 lanes each), rows interleaved in
+ * granules of 8 entries so that a warp reads 256 contiguous bytes per half-step: entry k of particle i is word
+ *   (i / 8) * 8 * pitch + (k / 8) * 64 + (i % 8) * 8 + slot(k % 8),   slot(e) = e < 4 ? 2 e : 2 (e - 4) + 1
+ * (the 64-bit word of a lane holds entries e and e + 4: one gather request covers 4 consecutive entries per particle).
+ * rows_dev: hx_shell_rows_words(nparticle, pitch) words (tiles + slack read ahead by the kernel; build initialises all);
+ * ends_dev: nparticle * HX_NSHELL uint16, 16-byte aligned; pitch: multiple of 32, > longest list, <= 512. */
 #define HX_NSHELL 8
 typedef struct hx_shell_rows {
     uint32_t* rows_dev;
@@ -215,6 +219,7 @@ typedef struct hx_shell_rows {
 } hx_shell_rows;
 /* delta[s] = skin * (s + 1) / HX_NSHELL */
 int hx_shell_rows_plan(float skin, hx_shell_rows* shells);
+size_t hx_shell_rows_words(size_t nparticle, unsigned pitch);
 /* largest entry of count_dev[0..n) into *max_dev (the caller picks the pitch from it) */
 int hx_count_max(const uint32_t* count_dev, size_t n, uint32_t* max_dev, void* stream);
 int hx_shell_rows_build(const hx_lj_params* potential, const uint32_t* g_neighbour_dev, size_t stride,
@@ -223,7 +228,7 @@ int hx_shell_rows_build(const hx_lj_params* potential, const uint32_t* g_neighbo
                         const hx_shell_rows* shells, void* stream);
 int hx_pair_force_shells(const hx_lj_params* potential, const hx_float4* position1_hi_dev,
                          const hx_float4* position2_hi_dev, const hx_shell_rows* shells, const hx_float4* r0_dev,
-                         size_t nparticle, const float box_length[3], int flags /* HX_FORCE_* bits */, int force_zero,
+                         size_t nparticle, const float box_length[3], int flags /* HX_FORCE_POSITIONS_REDUCED */, int force_zero,
                          hx_float4* force_dev, uint32_t* ctl_dev, float skin_half, void* stream);
 
 /* ---- f1: external one-body force, planar Lennard-Jones 9-3 walls -----------------------------------------------

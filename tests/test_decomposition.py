@@ -104,6 +104,9 @@ def single_gpu_reference(n, steps):
     from halmd_b200 import simulation
     s = simulation.lennard_jones_fluid(n, seed=21)            # same generator calls as dd_worker.gpu_parity
     p = s.particle
+    # the decomposed loop walks the public rows: the same summation order is what makes the runs comparable bit by bit
+    from halmd_b200 import _lib as hx
+    hx.check(hx.lib.hxm_neighbour_set_shell_rows(s.neighbour._h, 0))
 
     def snap():
         s.force.apply()

@@ -31,12 +31,23 @@ def make_shells(hx, dev, s, par, skin):
     pitch = (longest + 32) // 32 * 32
     sh = hx.ShellRows()
     hx.check(hx.lib.hx_shell_rows_plan(float(skin), C.byref(sh)))
-    d_rows = dev.up(np.full(n * pitch + 64, 0xDEADBEEF, dtype=np.uint32))
+    words = int(hx.lib.hx_shell_rows_words(n, pitch))
+    assert words >= (n + 7) // 8 * 8 * pitch + 256
+    d_rows = dev.up(np.full(words, 0xDEADBEEF, dtype=np.uint32))
     d_ends = dev.zeros(n * hx.NSHELL, np.uint16)
     sh.rows_dev, sh.ends_dev, sh.pitch = d_rows.data_ptr(), d_ends.data_ptr(), pitch
     hx.check(hx.lib.hx_shell_rows_build(C.byref(par), dev.p(s["d_nl"]), s["stride"], dev.p(d_count), dev.p(s["d_pos"]),
                                         dev.p(s["d_pos"]), n, hx.f3(s["L"]), C.byref(sh), dev.stream), "hx_shell_rows_build")
     return sh, d_rows, d_ends, pitch
+
+
+def decode_rows(flat, n, pitch):
+    """Private rows from the tile-interleaved layout documented in include/halmd_b200.h (hx_shell_rows)."""
+    i = np.arange(n, dtype=np.int64)[:, None]
+    k = np.arange(pitch, dtype=np.int64)[None, :]
+    e = k % 8
+    slot = np.where(e < 4, 2 * e, 2 * (e - 4) + 1)
+    return flat[(i // 8) * 8 * pitch + (k // 8) * 64 + (i % 8) * 8 + slot]
 
 
 def lj(hx, oracle, nt, eps, sigma, trunc, cut, h=0.005):
@@ -56,9 +67,10 @@ def test_shell_rows_are_a_stable_regrouping(hx, oracle, dev, n, rho, rc, skin, o
     nt = s["nt"]
     par, _ = lj(hx, oracle, nt, eps, sigma, 2, [2.5] * (nt * nt))
     sh, d_rows, d_ends, pitch = make_shells(hx, dev, s, par, skin)
-    rows = dev.down(d_rows)
-    assert np.all(rows[n * pitch:] == 0)                       # slack behind the last row
-    rows = rows[:n * pitch].reshape(n, pitch)
+    flat = dev.down(d_rows)
+    assert np.all(flat[(n + 7) // 8 * 8 * pitch:] == 0)       # slack behind the last tile
+    assert not np.any(flat == 0xDEADBEEF)                      # every word the kernel may read is initialised
+    rows = decode_rows(flat, n, pitch)
     ends = dev.down(d_ends).reshape(n, hx.NSHELL).astype(np.int64)
     cnt = s["count"].astype(np.int64)
     pub = s["nl"].reshape(n, s["stride"])
@@ -153,16 +165,18 @@ def close(f, g, n, tol):
     return rel
 
 
-@pytest.mark.parametrize("lanes", [2, 4, 8])
+@pytest.mark.parametrize("n", [16000, 15997])
 @pytest.mark.parametrize("trunc", [0, 1, 2, 3])
 @pytest.mark.parametrize("dmax", [0.0, 0.03, 0.12, 0.249])
-def test_shell_force_equals_full_walk(hx, oracle, dev, lanes, trunc, dmax):
+def test_shell_force_equals_full_walk(hx, oracle, dev, n, trunc, dmax):
     """Lists built at r0, positions moved by up to dmax: the prefix walk must not lose a pair inside the cutoff
-    (same forces as the full walk up to the order of the compensated sums) and match the oracle."""
-    if lanes != 4 and (trunc != 2 or dmax not in (0.12,)):
-        pytest.skip("lane variants are exercised for smooth_r4 at one displacement")
+    (same forces as the full walk up to the order of the compensated sums) and match the oracle.  n = 15997: the last
+    tile of 8 particles is incomplete."""
+    if n != 16000 and (trunc != 2 or dmax not in (0.12,)):
+        pytest.skip("the incomplete last tile is exercised for smooth_r4 at one displacement")
     skin = 0.5
-    s = build_lists(hx, oracle, dev, 16000, 0.8442, 73, [2.5], skin, 0.5, 0.4, layout=1, fill_all=0, reduce=True)
+    lanes = 4
+    s = build_lists(hx, oracle, dev, n, 0.8442, 73, [2.5], skin, 0.5, 0.4, layout=1, fill_all=0, reduce=True)
     par, opar = lj(hx, oracle, 1, [1.0], [1.0], trunc, [2.5])
     sh, d_rows, d_ends, pitch = make_shells(hx, dev, s, par, skin)
     p, max_rr = displaced(s, np.random.default_rng(7), dmax)
@@ -172,14 +186,14 @@ def test_shell_force_equals_full_walk(hx, oracle, dev, lanes, trunc, dmax):
     f, ctl_out = shell_force(hx, dev, s, par, sh, d_pos, s["d_pos"], ctl, skin, lanes=lanes)
     assert ctl_out[1] == 0 and ctl_out[2] == 1                 # not halted, one step counted
     g = full_force(hx, dev, s, par, d_pos, lanes=lanes)
-    rel = close(f, g, n, 3e-7)
+    rel = close(f, g, n, 5e-7)
     assert np.median(rel) == 0.0                               # same pairs, same arithmetic: typically identical bits
     close(f, oracle_force(oracle, s, opar, p), n, ORACLE_TOL)
     # the reduced-positions fast path changes nothing; without r0 / ctl the whole row is walked
     f2, _ = shell_force(hx, dev, s, par, sh, d_pos, s["d_pos"], ctl, skin, lanes=lanes, flags=hx.FORCE_POSITIONS_REDUCED)
     assert f2.tobytes() == f.tobytes()
     f3, _ = shell_force(hx, dev, s, par, sh, d_pos, None, None, skin, lanes=lanes)
-    close(f3, g, n, 3e-7)
+    close(f3, g, n, 5e-7)
 
 
 def test_shell_force_walks_a_prefix_only(hx, oracle, dev):
@@ -211,7 +225,7 @@ def test_shell_force_binary_mixture(hx, oracle, dev):
         d_pos = dev.up(p)
         ctl = np.array([max_rr.view(np.uint32), 0, 0, 0], dtype=np.uint32)
         f, _ = shell_force(hx, dev, s, par, sh, d_pos, s["d_pos"], ctl, skin)
-        close(f, full_force(hx, dev, s, par, d_pos), s["n"], 3e-7)
+        close(f, full_force(hx, dev, s, par, d_pos), s["n"], 5e-7)
         close(f, oracle_force(oracle, s, opar, p), s["n"], ORACLE_TOL)
 
 
@@ -250,5 +264,5 @@ def test_shell_rows_256k(hx, oracle, dev):
     d_pos = dev.up(p)
     ctl = np.array([max_rr.view(np.uint32), 0, 0, 0], dtype=np.uint32)
     f, _ = shell_force(hx, dev, s, par, sh, d_pos, s["d_pos"], ctl, skin, flags=hx.FORCE_POSITIONS_REDUCED)
-    close(f, full_force(hx, dev, s, par, d_pos, flags=hx.FORCE_POSITIONS_REDUCED), s["n"], 3e-7)
+    close(f, full_force(hx, dev, s, par, d_pos, flags=hx.FORCE_POSITIONS_REDUCED), s["n"], 5e-7)
     close(f, oracle_force(oracle, s, opar, p), s["n"], ORACLE_TOL)
