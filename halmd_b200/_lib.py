@@ -17,6 +17,7 @@ LAYOUT_COLUMN, LAYOUT_ROW = 0, 1
 FORCE_POSITIONS_REDUCED = 0x100     # OR-ed into `layout` of the pair-force calls (include/halmd_b200.h)
 FORCE_SCALAR = 0x200
 NSHELL = 8
+THERMO_DOUBLES = 8 + 8 * 296     # words of the output / scratch buffer of hx_thermodynamics
 
 
 def FORCE_LANES(lanes):
@@ -141,6 +142,7 @@ _protos = {
     "hx_correlate_block": (C.c_int, [C.c_int, P, P, C.c_uint, SZ, P, P, SZ, P]),
     "hx_density_modes": (C.c_int, [P, SZ, P, C.c_uint, P, P]),
     "hx_thermodynamics": (C.c_int, [P, P, P, SZ, SZ, P, P]),
+    "hx_wavevector_pick": (C.c_int, [D3, C.c_uint, D3, C.c_double, C.c_uint, U3, D3, C.c_uint, U3]),
     "hx_ctl_reset": (C.c_int, [P, P]),
     "hx_nlist_build2": (C.c_int, [P, U3, C.c_uint, P, SZ, SZ, F3, C.c_uint, C.c_uint, F3, P, C.c_uint, SZ,
                                   C.c_int, C.c_int, P, P, P]),

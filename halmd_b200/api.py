@@ -532,50 +532,42 @@ class _thermodynamics:
         return core.get().thermodynamics()
 
 
+class _semilog_grid:
+    """observables.utility.semilog_grid{start, stop, decimation} (halmd/observables/utility/semilog_grid.cpp:31-52):
+    linear grid from `start` with spacing `start`, the spacing doubled after every `decimation` points (0: never)."""
+
+    def __init__(self, start=None, stop=None, decimation=0):
+        grid, h, x, i = [], float(start), float(start), 0
+        while x < stop:
+            grid.append(x)
+            x += h
+            i += 1
+            if decimation > 0 and i % decimation == 0:
+                h *= 2
+        self.value = grid
+
+
 class _wavevector:
     """observables.utility.wavevector{box, wavenumber, tolerance, max_count} — reciprocal lattice vectors grouped in
     shells (halmd/observables/utility/wavevector.cpp:40-120, halmd/algorithm/host/pick_lattice_points.hpp:62-160)."""
 
     def __init__(self, box=None, wavenumber=None, tolerance=0.01, max_count=7, filter=None):
-        from math import gcd
-        L = box.length
-        unit = 2 * np.pi / L
         wavenumber = [float(q) for q in wavenumber]
-        filt = np.ones(3, dtype=int) if filter is None else np.asarray(filter, dtype=int)
-        r_max = max(wavenumber) * (1 + tolerance)
-        msum = np.cumsum([int(r_max / u) for u in unit])
-        count = [0] * len(wavenumber)
-        picked = [[] for _ in wavenumber]
-        idx = [0, 0, 0]
-        while idx[2] <= msum[2]:
-            hkl = np.array([idx[0], idx[1] - idx[0], idx[2] - idx[1]])
-            # (the reference computes hkl in unsigned arithmetic: negative entries wrap to huge values whose
-            # lattice direction never matches a wavenumber, i.e. they are skipped)
-            if np.all(hkl >= 0) and np.all(hkl * filt == hkl) and gcd(gcd(int(hkl[0]), int(hkl[1])), int(hkl[2])) == 1:
-                r0 = unit * hkl
-                r0_norm = float(np.linalg.norm(r0))
-                for i, q in enumerate(wavenumber):
-                    if count[i] < max_count:
-                        n = int(np.floor(q / r0_norm + 0.5))
-                        if n > 0 and abs(n * r0_norm - q) <= q * tolerance:
-                            picked[i].append(n * r0)
-                            count[i] += 1
-            idx[0] += 1
-            for j in range(2):
-                if idx[j] <= msum[j]:
-                    break
-                idx[j] = 0
-                idx[j + 1] += 1
-        self.wavenumber = [q for q, pts in zip(wavenumber, picked) if pts]
-        self.shell = []
-        vecs = []
-        for pts in picked:
-            if pts:
-                self.shell.append((len(vecs), len(vecs) + len(pts)))
-                vecs.extend(pts)
-        if not vecs:
-            raise ValueError("Constraints on wavevectors are incompatible with geometry of simulation box.")
-        self.value = np.asarray(vecs, dtype=np.float64)
+        nw = len(wavenumber)
+        cap = nw * int(max_count)
+        vec = np.zeros((max(cap, 1), 3))
+        offs = (C.c_uint * (nw + 1))()
+        filt = None if filter is None else (C.c_uint * 3)(*[int(x) for x in filter])
+        check(lib.hx_wavevector_pick((C.c_double * nw)(*wavenumber), nw, box._d3(), float(tolerance), int(max_count), filt,
+                                     vec.ctypes.data_as(hx.D3), cap, offs), "observables.utility.wavevector")
+        offs = list(offs)
+        keep = [i for i in range(nw) if offs[i + 1] > offs[i]]       # wavevector.cpp:103-118: empty shells are discarded
+        self.wavenumber = [wavenumber[i] for i in keep]
+        self.shell, rows = [], []
+        for i in keep:
+            self.shell.append((len(rows), len(rows) + offs[i + 1] - offs[i]))
+            rows.extend(range(offs[i], offs[i + 1]))
+        self.value = np.ascontiguousarray(vec[rows])
 
 
 class _density_mode:
@@ -630,6 +622,8 @@ class _blocking_scheme(_Handle):
     def __init__(self, max_lag=None, every=None, size=10, shift=None, separation=None, wavevector=None):
         super().__init__()
         c = core.get()
+        # the C object refers to the core and, through it, to the integrator: keep both alive as long as this handle
+        self._core, self._integrator = c, c.integrator
         dt = c.integrator.timestep
         shift = int(np.floor(np.sqrt(size))) if shift is None else int(shift)        # blocking_scheme.lua.in
         separation = size if separation is None else int(separation)
@@ -701,7 +695,7 @@ mdsim = _NS(
 observables = _NS(
     sampler=_sampler(),
     thermodynamics=_thermodynamics,
-    utility=_NS(wavevector=_wavevector),
+    utility=_NS(wavevector=_wavevector, semilog_grid=_semilog_grid),
     density_mode=_density_mode,
     ssf=_ssf,
     dynamics=_NS(blocking_scheme=_blocking_scheme),

@@ -1,5 +1,10 @@
 // Library plumbing + host-side sizing formulas of the reference modules.
 #include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <iterator>
+#include <map>
+#include <vector>
 #include <cstdarg>
 #include <cstdio>
 #include <cmath>
@@ -244,6 +249,89 @@ double hx_hoover_chain_energy(const hx_hoover_chain* c, size_t nparticle)
     double en = c->temperature * (c->dof * c->xi[0] + c->xi[1]);
     for (int i = 0; i < 2; ++i) en += c->mass_xi[i] * c->v_xi[i] * c->v_xi[i] / 2;
     return en / static_cast<double>(nparticle);
+}
+
+
+// observables.utility.wavevector (halmd/observables/utility/wavevector.cpp:40-123) on top of
+// algorithm::host::pick_lattice_points_from_shell (halmd/algorithm/host/pick_lattice_points.hpp:62-160): reciprocal
+// lattice vectors n (h, k, l) * 2 pi / L with coprime Miller indices whose magnitude matches one of the wavenumbers
+// within the relative tolerance, at most max_count per wavenumber, generated in the order of increasing h + k + l
+// (index tuple (h, h + k, h + k + l) counted like an odometer) — that order decides which points a full shell keeps.
+// Output: vectors grouped by wavenumber in the order of `wavenumber` (wavenumbers without a vector get an empty shell:
+// shell_offsets[i] == shell_offsets[i + 1]; the caller drops them as wavevector.cpp:103-118 does).
+int hx_wavevector_pick(const double* wavenumber, unsigned nwavenumber, const double box_length[3], double tolerance,
+                       unsigned max_count, const unsigned* filter, double* vectors_out, unsigned capacity,
+                       unsigned* shell_offsets_out)
+{
+    if (!wavenumber || !box_length || !vectors_out || !shell_offsets_out || nwavenumber == 0) {
+        set_error("hx_wavevector_pick: invalid argument");
+        return HX_E_INVALID;
+    }
+    unsigned const one[3] = {1, 1, 1};
+    if (!filter) filter = one;
+    for (int d = 0; d < 3; ++d)
+        if (filter[d] > 1) { set_error("filter values must be 0 or 1"); return HX_E_INVALID; }
+    double unit[3];
+    for (int d = 0; d < 3; ++d) unit[d] = 2 * M_PI / box_length[d];
+    double r_max = 0;
+    for (unsigned i = 0; i < nwavenumber; ++i) r_max = std::max(r_max, wavenumber[i]);
+    r_max *= 1 + tolerance;
+    unsigned long long sum_max[3];
+    for (int d = 0; d < 3; ++d) sum_max[d] = (unit[d] == 0) ? 0 : static_cast<unsigned int>(r_max / unit[d]);
+    sum_max[1] += sum_max[0];
+    sum_max[2] += sum_max[1];
+    // wavevector.cpp:78-87 collects the points in a multimap keyed by the wavenumber through std::inserter(map, end):
+    // the hint of every insertion is the position behind the previous one, and an element goes "as close as possible
+    // to the position just prior to the hint" — which fixes the order of the vectors inside a shell (the first
+    // wavenumber keeps the generation order, later ones mostly do not).  The same container and inserter are used here.
+    struct vec3d { double v[3]; };
+    std::multimap<unsigned, vec3d> picked;
+    auto out = std::inserter(picked, picked.end());
+    std::vector<unsigned> count(nwavenumber, 0);
+    auto gcd = [](unsigned long long a, unsigned long long b) { while (b) { unsigned long long t = b; b = a % b; a = t; } return a; };
+    unsigned long long idx[3] = {0, 0, 0};
+    while (idx[2] <= sum_max[2]) {
+        // (the reference forms h, k, l in unsigned arithmetic; tuples with idx[j] < idx[j-1] wrap to huge indices whose
+        // direction never matches a wavenumber: they are skipped here)
+        if (idx[1] >= idx[0] && idx[2] >= idx[1]) {
+            unsigned long long const hkl[3] = {idx[0], idx[1] - idx[0], idx[2] - idx[1]};
+            bool const pass = hkl[0] * filter[0] == hkl[0] && hkl[1] * filter[1] == hkl[1] && hkl[2] * filter[2] == hkl[2];
+            if (pass && gcd(hkl[0], gcd(hkl[1], hkl[2])) == 1) {
+                double const r0[3] = {unit[0] * hkl[0], unit[1] * hkl[1], unit[2] * hkl[2]};
+                double const r0_norm = std::sqrt(r0[0] * r0[0] + r0[1] * r0[1] + r0[2] * r0[2]);
+                // (directions longer than the largest radius match nothing: n * r0_norm > r * (1 + tolerance) for n >= 1)
+                for (unsigned i = 0; r0_norm <= r_max && i < nwavenumber; ++i) {
+                    if (count[i] < max_count) {
+                        unsigned int const n = static_cast<unsigned int>(std::floor(wavenumber[i] / r0_norm + 0.5));
+                        if (n > 0 && std::abs(n * r0_norm - wavenumber[i]) <= wavenumber[i] * tolerance) {
+                            *out++ = std::make_pair(i, vec3d{{n * r0[0], n * r0[1], n * r0[2]}});
+                            ++count[i];
+                        }
+                    }
+                }
+            }
+        }
+        ++idx[0];
+        for (int j = 0; j < 2; ++j) {
+            if (idx[j] <= sum_max[j]) break;
+            idx[j] = 0;
+            ++idx[j + 1];
+        }
+    }
+    unsigned total = 0;
+    for (unsigned i = 0; i < nwavenumber; ++i) {
+        shell_offsets_out[i] = total;
+        if (total + count[i] > capacity) { set_error("hx_wavevector_pick: output capacity %u too small", capacity); return HX_E_INVALID; }
+        auto const range = picked.equal_range(i);
+        for (auto it = range.first; it != range.second; ++it, ++total)
+            for (int d = 0; d < 3; ++d) vectors_out[3 * static_cast<size_t>(total) + d] = it->second.v[d];
+    }
+    shell_offsets_out[nwavenumber] = total;
+    if (total == 0) {
+        set_error("Constraints on wavevectors are incompatible with geometry of simulation box.");
+        return HX_E_INVALID;
+    }
+    return HX_OK;
 }
 
 } // extern "C"

@@ -83,12 +83,28 @@ struct hxm_particle {
     // after positions were written from outside (HX_FORCE_POSITIONS_REDUCED)
     bool reduced = false;
     double* io_dev = nullptr;        // [3 n] staging of double-precision samples (particle get / set)
+    void* scratch = nullptr;         // grow-only device scratch of the observables (wavevectors, density modes)
+    size_t scratch_bytes = 0;
+
+    int get_scratch(size_t bytes, void** out)
+    {
+        if (bytes > scratch_bytes) {
+            if (scratch) cudaFree(scratch);
+            scratch = nullptr;
+            scratch_bytes = 0;
+            HXM_CUDA(cudaMalloc(&scratch, bytes));
+            scratch_bytes = bytes;
+        }
+        *out = scratch;
+        return 0;
+    }
 
     ~hxm_particle()
     {
         dev_free(pos); dev_free(vel); dev_free(image); dev_free(force); dev_free(pos_b); dev_free(vel_b);
         dev_free(image_b); dev_free(en_pot); dev_free(stress); dev_free(id); dev_free(rid); dev_free(id_b);
         dev_free(io_dev);
+        if (scratch) cudaFree(scratch);
     }
 };
 
@@ -603,14 +619,32 @@ struct hxm_core {
 
 // ---- blocking scheme ------------------------------------------------------------------------------------------------------------
 struct hxm_blocking {
+    // device buffers of retired samples are reused: cudaMalloc / cudaFree of a 16 MB buffer costs tens of milliseconds,
+    // far more than the sampling kernels themselves
+    struct buffer_pool {
+        std::vector<float4*> free_list;
+        ~buffer_pool() { for (float4* p : free_list) cudaFree(p); }
+        int get(float4** out, size_t n)
+        {
+            if (!free_list.empty()) { *out = free_list.back(); free_list.pop_back(); return 0; }
+            return dev_alloc(out, n);
+        }
+    };
     struct sample {
+        std::shared_ptr<buffer_pool> pool;
         float4* positions = nullptr;         // unfolded positions in id order (device)
         float4* velocities = nullptr;        // velocities in id order (device)
         std::vector<double> rho;             // density modes (re, im) per wavevector
         uint64_t step = 0;
-        ~sample() { if (positions) cudaFree(positions); if (velocities) cudaFree(velocities); }
+        ~sample()
+        {
+            if (positions) pool->free_list.push_back(positions);
+            if (velocities) pool->free_list.push_back(velocities);
+        }
     };
+    std::shared_ptr<buffer_pool> pool = std::make_shared<buffer_pool>();
     hxm_core* core = nullptr;
+    double timestep = 0;                     // time step the sampling intervals were computed for
     unsigned block_size = 10, separation = 10;
     std::vector<uint64_t> interval, origin;
     std::vector<std::deque<std::shared_ptr<sample>>> blocks;
@@ -640,12 +674,13 @@ struct hxm_blocking {
         hxm_particle* p = core->integrator->particle;
         if (current && current->step == core->step) { out = current; return 0; }
         auto s = std::make_shared<sample>();
+        s->pool = pool;
         s->step = core->step;
-        HXM_TRY(dev_alloc(&s->positions, p->n));
+        HXM_TRY(pool->get(&s->positions, p->n));
         float* Lf = core->integrator->Lf;
         HXM_TRY(hx_sample_positions(reinterpret_cast<hx_float4*>(p->pos), reinterpret_cast<hx_float4*>(p->image), p->rid, p->n,
                                     Lf, reinterpret_cast<hx_float4*>(s->positions), p->st));
-        HXM_TRY(dev_alloc(&s->velocities, p->n));
+        HXM_TRY(pool->get(&s->velocities, p->n));
         HXM_TRY(hx_sample_velocities(reinterpret_cast<hx_float4*>(p->vel), p->rid, p->n,
                                      reinterpret_cast<hx_float4*>(s->velocities), p->st));
         if (nq > 0) {
@@ -724,6 +759,11 @@ struct hxm_blocking {
     // blocking_scheme::sample (blocking_scheme.cpp:129-161)
     int do_sample()
     {
+        // blocking_scheme.cpp:136-139
+        if (core->integrator->timestep != timestep) {
+            set_error("blocking scheme does not allow variable time step");
+            return HX_E_INVALID;
+        }
         uint64_t const step = core->step;
         for (unsigned i = 0; i < interval.size(); ++i) {
             if (step >= origin[i] && (step - origin[i]) % interval[i] == 0) {
@@ -1264,7 +1304,7 @@ int hxm_integrator_hoover_create(hxm_particle* particle, hxm_force* force, const
     i->temperature = temperature;
     i->resonance_frequency = resonance_frequency;
     HXM_TRY(hx_hoover_chain_init(&i->chain, particle->n, 3, temperature, resonance_frequency));
-    HXM_TRY(dev_alloc(&i->d_hoover, 8));
+    HXM_TRY(dev_alloc(&i->d_hoover, HX_THERMO_DOUBLES));
     HXM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&i->h_hoover), 8 * sizeof(double)));
     *out = guard.release();
     return 0;
@@ -1292,7 +1332,7 @@ int hxm_core_create(hxm_integrator* integrator, hxm_core** out)
     if (!integrator || !out) return HX_E_INVALID;
     auto c = std::unique_ptr<hxm_core>(new hxm_core);
     c->integrator = integrator;
-    HXM_TRY(dev_alloc(&c->d_thermo, 8));
+    HXM_TRY(dev_alloc(&c->d_thermo, HX_THERMO_DOUBLES));
     HXM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_thermo), 8 * sizeof(double)));
     *out = c.release();
     return 0;
@@ -1326,18 +1366,16 @@ int hxm_core_thermodynamics(hxm_core* c, double out[10]) { return (c && out) ? c
 int hxm_density_modes(hxm_particle* p, const float* wavevector_host, unsigned nq, double* rho_host)
 {
     if (!p || !wavevector_host || !rho_host || nq == 0) { set_error("density_mode: invalid argument"); return HX_E_INVALID; }
-    float* q = nullptr;
-    double* rho = nullptr;
-    HXM_TRY(dev_alloc(&q, static_cast<size_t>(3) * nq));
-    int rc = dev_alloc(&rho, static_cast<size_t>(2) * nq);
-    if (rc == 0) rc = static_cast<int>(cudaMemcpyAsync(q, wavevector_host, sizeof(float) * 3 * nq, cudaMemcpyHostToDevice, p->st));
-    if (rc == 0) rc = hx_density_modes(reinterpret_cast<const hx_float4*>(p->pos), p->n, q, nq, rho, p->st);
-    if (rc == 0) rc = static_cast<int>(cudaMemcpyAsync(rho_host, rho, sizeof(double) * 2 * nq, cudaMemcpyDeviceToHost, p->st));
-    if (rc == 0) rc = static_cast<int>(cudaStreamSynchronize(p->st));
-    dev_free(q);
-    dev_free(rho);
-    if (rc != 0) set_error("density_mode: failed (code %d)", rc);
-    return rc;
+    void* scratch = nullptr;
+    size_t const rho_bytes = sizeof(double) * 2 * nq;
+    HXM_TRY(p->get_scratch(rho_bytes + sizeof(float) * 3 * nq, &scratch));
+    double* rho = static_cast<double*>(scratch);
+    float* q = reinterpret_cast<float*>(static_cast<char*>(scratch) + rho_bytes);
+    HXM_CUDA(cudaMemcpyAsync(q, wavevector_host, sizeof(float) * 3 * nq, cudaMemcpyHostToDevice, p->st));
+    HXM_TRY(hx_density_modes(reinterpret_cast<const hx_float4*>(p->pos), p->n, q, nq, rho, p->st));
+    HXM_CUDA(cudaMemcpyAsync(rho_host, rho, rho_bytes, cudaMemcpyDeviceToHost, p->st));
+    HXM_CUDA(cudaStreamSynchronize(p->st));
+    return 0;
 }
 
 int hxm_blocking_create(hxm_core* core, double max_lag_time, double resolution, unsigned block_size, unsigned shift,
@@ -1356,6 +1394,7 @@ int hxm_blocking_create(hxm_core* core, double max_lag_time, double resolution, 
     b->block_size = block_size;
     b->separation = separation;
     double const timestep = core->integrator->timestep;
+    b->timestep = timestep;
     uint64_t max_interval = static_cast<uint64_t>(std::round(max_lag_time / timestep));
     uint64_t s = static_cast<uint64_t>(std::round(resolution / timestep));
     if (s == 0) { set_error("Resolution must be at least one time step."); return HX_E_INVALID; }

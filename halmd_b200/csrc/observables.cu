@@ -181,21 +181,27 @@ __global__ void k_density_modes(const float4* __restrict__ pos, unsigned n, cons
 }
 
 constexpr unsigned TH_THREADS = 256;
+constexpr unsigned TH_BLOCKS = HX_THERMO_BLOCKS;
 
+// Thermodynamic sums with the per-particle terms of the reference's accumulators (thermodynamics_kernel.cu:35-97) as its
+// build evaluates them: inner_prod(v, v) in float (FMUL + 2 FFMA), the product with the mass fused into the
+// double-single accumulation, i.e. exact — here exact in double.  Block partials go to scratch and are combined by the
+// last block to finish, in block order: the sums do not depend on the order in which blocks run.
 __global__ void k_thermodynamics(const float4* __restrict__ vel, const float* __restrict__ en_pot,
                                  const float* __restrict__ stress, size_t stress_stride, unsigned n,
                                  double* __restrict__ out)
 {
     __shared__ double s_red[TH_THREADS / 32][7];
+    __shared__ bool s_last;
     double acc[7] = {0., 0., 0., 0., 0., 0., 0.};
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 v = vel[i];
-        // mass * inner_prod(v, v) in float (thermodynamics_kernel.cu:35-41)
-        acc[0] += static_cast<double>(__fmul_rn(v.w, norm2(v.x, v.y, v.z)));
-        acc[1] += static_cast<double>(__fmul_rn(v.w, v.x));
-        acc[2] += static_cast<double>(__fmul_rn(v.w, v.y));
-        acc[3] += static_cast<double>(__fmul_rn(v.w, v.z));
-        acc[4] += static_cast<double>(v.w);
+        double const m = static_cast<double>(v.w);
+        acc[0] += m * static_cast<double>(norm2(v.x, v.y, v.z));
+        acc[1] += m * static_cast<double>(v.x);
+        acc[2] += m * static_cast<double>(v.y);
+        acc[3] += m * static_cast<double>(v.z);
+        acc[4] += m;
         if (en_pot) acc[5] += static_cast<double>(en_pot[i]);
         if (stress) {
             acc[6] += static_cast<double>(stress[i]) + static_cast<double>(stress[stress_stride + i])
@@ -209,10 +215,22 @@ __global__ void k_thermodynamics(const float4* __restrict__ vel, const float* __
         for (int k = 0; k < 7; ++k) s_red[threadIdx.x >> 5][k] = acc[k];
     }
     __syncthreads();
+    double* const partial = out + 8;                  // [TH_BLOCKS][8]
+    unsigned* const ticket = reinterpret_cast<unsigned*>(out + 7);
     if (threadIdx.x < 7) {
         double t = 0.;
         for (unsigned w = 0; w < TH_THREADS / 32; ++w) t += s_red[w][threadIdx.x];
-        atomicAdd(&out[threadIdx.x], t);
+        partial[blockIdx.x * 8 + threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x < 7) {
+        __threadfence();
+        double t = 0.;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(&partial[b * 8 + threadIdx.x]);
+        out[threadIdx.x] = t;
     }
 }
 
@@ -312,7 +330,7 @@ int hx_thermodynamics(const hx_float4* velocity_hi_dev, const float* en_pot_dev,
     if (err != cudaSuccess) { set_error("hx_thermodynamics: %s", cudaGetErrorString(err)); return static_cast<int>(err); }
     if (nparticle == 0) return HX_OK;
     unsigned blocks = div_up(nparticle, TH_THREADS);
-    if (blocks > 296) blocks = 296;
+    if (blocks > TH_BLOCKS) blocks = TH_BLOCKS;
     k_thermodynamics<<<blocks, TH_THREADS, 0, st>>>(reinterpret_cast<const float4*>(velocity_hi_dev), en_pot_dev,
                                                    stress_dev, stress_stride, static_cast<unsigned>(nparticle), out_dev);
     return check_launch("k_thermodynamics");

@@ -267,7 +267,7 @@ class DecomposedSystem:
         self.cell_count = z(self.ncells, dtype=i32)
         self.nl = torch.empty(self.own_cap * self.stride, dtype=i32, device=dev)
         self.nl_count = z(self.own_cap, dtype=i32)
-        self.thermo = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.thermo = torch.zeros(hx.THERMO_DOUBLES, dtype=torch.float64, device=dev)
         self.send_idx = {"left": z(0, dtype=i32), "right": z(0, dtype=i32)}
         self.send_buf = {"left": z(0, 4), "right": z(0, 4)}
         self.n_ghost_from = {"left": 0, "right": 0}
@@ -583,7 +583,7 @@ class DecomposedSystem:
         self.force_valid = True
         hx.check(self.lib.hx_thermodynamics(self._p(self.vel), self._p(self.en_pot), self._p(self.stress), self.cap, self.n_own,
                                             self._p(self.thermo), self.st), "thermodynamics")
-        t = self.thermo.clone()
+        t = self.thermo[:8].clone()
         self.ex.allreduce(t, "sum")
         s = t.cpu().numpy()
         N = float(self.n_global)

@@ -131,6 +131,40 @@ def kob_andersen_mixture(n, density=1.2, temperature=0.7, timestep=0.001, skin=0
     return System(box, particle, potential, force, integ)
 
 
+def wetting_slab(n, D=None, density=0.6, temperature=0.9, timestep=0.001, seed=5, rate=5.0, integrator="verlet_nvt_andersen"):
+    """BASELINE config 5 (examples/definitions/slit_pore.lua:51-67): LJ fluid (smooth_r4, r_c = 2.5) between two planar
+    Lennard-Jones walls with normals -+x at x = +-(D + 1) / 2, periodic in y and z; box (D + 10) x L_y x L_y with
+    L_y from the slab density.  D defaults to the value that makes the slab about cubic."""
+    rng = np.random.default_rng(seed)
+    if D is None:
+        D = float(np.round((n / density) ** (1.0 / 3)))
+    Lx = D + 10.0
+    Ly = (n / density / D) ** 0.5
+    box = mdsim.box(length=[Lx, Ly, Ly])
+    p = mdsim.particle(dimension=3, particles=n, species=1)
+    ext = np.array([D - 2.0, Ly, Ly])
+    a = (np.prod(ext) / n) ** (1 / 3)                      # grid with near-equal spacing in the slab |x| < D/2 - 1
+    mx = max(int(ext[0] / a), 1)
+    my = int(np.ceil(np.sqrt(n / mx)))
+    g = np.stack(np.meshgrid(np.arange(mx), np.arange(my), np.arange(my), indexing="ij"), -1).reshape(-1, 3)
+    g = g[rng.permutation(len(g))[:n]].astype(np.float64)
+    p.set("position", ((g + 0.5) / np.array([mx, my, my]) * ext - 0.5 * ext).astype(np.float32))
+    v = rng.normal(scale=np.sqrt(temperature), size=(n, 3))
+    p.set("velocity_ds", v - v.mean(axis=0))
+    pot = mdsim.potentials.pair.lennard_jones().truncate("smooth_r4", cutoff=2.5, h=0.005)
+    force = mdsim.forces.pair(box=box, particle=p, potential=pot)
+    if integrator == "verlet":
+        integ = mdsim.integrators.verlet(box=box, particle=p, timestep=timestep)
+    else:
+        integ = mdsim.integrators.verlet_nvt_andersen(box=box, particle=p, timestep=timestep, temperature=temperature, rate=rate, seed=seed)
+    wall = mdsim.potentials.external.planar_wall(offset=[-(D + 1) / 2] * 2, surface_normal=[[-1, 0, 0], [1, 0, 0]], epsilon=1.0,
+                                                 sigma=1.0, wetting=1.0, cutoff=2.5, smoothing=0.005, species=1)
+    mdsim.forces.external(box=box, particle=p, potential=wall)
+    s = System(box, p, pot, force, integ)
+    s.D = D
+    return s
+
+
 def decomposed_lj_fluid(n, rank, nranks, density=0.8442, temperature=1.2, cutoff=2.5, truncation="smooth_r4", h=0.005,
                         timestep=0.001, skin=0.5, seed=1, integrator="verlet", rate=2.0, group=None, chunk=1 << 22,
                         lanes=4):

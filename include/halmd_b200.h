@@ -354,12 +354,25 @@ int hx_correlate_block(int kind, const hx_float4* first_dev, const hx_float4* co
 /* rho_dev[2*q + {0,1}] = (sum cos q.r, -sum sin q.r) as doubles; q_dev: float[3*nq] */
 int hx_density_modes(const hx_float4* position_hi_dev, size_t nparticle, const float* q_dev,
                      unsigned nq, double* rho_dev, void* stream);
+/* observables.utility.wavevector{box, wavenumber, tolerance, max_count, filter} (halmd/observables/utility/wavevector.cpp:40-123,
+ * halmd/algorithm/host/pick_lattice_points.hpp:62-160), host side, no device work: wavevectors n (h, k, l) 2 pi / L with
+ * coprime (h, k, l) whose magnitude matches wavenumber[i] within the relative tolerance, at most max_count per wavenumber,
+ * preferring small h + k + l.  vectors_out: 3 * capacity doubles, grouped by wavenumber; shell_offsets_out: nwavenumber + 1
+ * offsets (an empty shell marks a wavenumber the caller must drop).  filter (3 entries 0 / 1) may be NULL. */
+int hx_wavevector_pick(const double* wavenumber, unsigned nwavenumber, const double box_length[3], double tolerance,
+                       unsigned max_count, const unsigned* filter, double* vectors_out, unsigned capacity,
+                       unsigned* shell_offsets_out);
+
 /* thermodynamic sums over particles i < n, as doubles:
  * out[0]=sum m v^2, out[1..3]=sum m v, out[4]=sum m, out[5]=sum en_pot, out[6]=sum virial trace
- * (halmd/observables/gpu/thermodynamics_kernel.cu:35-97).  en_pot/stress may be NULL. */
+ * (halmd/observables/gpu/thermodynamics_kernel.cu:35-97).  en_pot/stress may be NULL.
+ * out_dev holds HX_THERMO_DOUBLES doubles: the 8 result words, then scratch for the block partials, which are
+ * combined in block order (results do not depend on the scheduling of blocks). */
+#define HX_THERMO_BLOCKS 296
+#define HX_THERMO_DOUBLES (8 + 8 * HX_THERMO_BLOCKS)
 int hx_thermodynamics(const hx_float4* velocity_hi_dev, const float* en_pot_dev,
                       const float* stress_dev, size_t stress_stride, size_t nparticle,
-                      double* out_dev /*8*/, void* stream);
+                      double* out_dev /* HX_THERMO_DOUBLES */, void* stream);
 
 /* ---- step-loop support (device-resident rebuild decision) ------------------------------------
  * The reference copies 64 floats to the host every step to decide whether the neighbour lists

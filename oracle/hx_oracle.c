@@ -911,10 +911,12 @@ void oracle_thermodynamics(const f4* vel, const float* en_pot, const float* stre
 {
     for (int k = 0; k < 8; ++k) out[k] = 0;
     for (size_t i = 0; i < n; ++i) {
-        out[0] += (double)(vel[i].w * norm2(vel[i].x, vel[i].y, vel[i].z));
-        out[1] += (double)(vel[i].w * vel[i].x);
-        out[2] += (double)(vel[i].w * vel[i].y);
-        out[3] += (double)(vel[i].w * vel[i].z);
+        /* thermodynamics_kernel.cu:35-97 as built (--fmad=true): inner_prod(v, v) in float, the product with the mass
+         * fused into the double-single accumulation, i.e. unrounded */
+        out[0] += (double)vel[i].w * (double)norm2(vel[i].x, vel[i].y, vel[i].z);
+        out[1] += (double)vel[i].w * (double)vel[i].x;
+        out[2] += (double)vel[i].w * (double)vel[i].y;
+        out[3] += (double)vel[i].w * (double)vel[i].z;
         out[4] += (double)vel[i].w;
         if (en_pot) out[5] += (double)en_pot[i];
         if (stress) out[6] += (double)stress[i] + (double)stress[stress_stride + i] + (double)stress[2 * stress_stride + i];

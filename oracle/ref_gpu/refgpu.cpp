@@ -33,6 +33,7 @@
 #include <halmd/observables/dynamics/velocity_autocorrelation.hpp>
 #include <halmd/observables/gpu/density_mode_kernel.hpp>
 #include <halmd/observables/gpu/dynamics/tagged_particle.hpp>
+#include <halmd/observables/gpu/thermodynamics_kernel.hpp>
 
 #include <algorithm>
 #include <cstdint>
@@ -40,58 +41,9 @@
 #include <type_traits>
 #include <vector>
 
-using namespace halmd;
-using namespace halmd::mdsim::gpu;
+#include "refgpu_util.hpp"
 
-#define RG_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "refgpu: %s: %s\n", #x, cudaGetErrorString(e_)); return static_cast<int>(e_); } } while (0)
-// every launch block is bracketed by events: refgpu_last_kernel_ms() returns the device time of the last one (the
-// reference's kernels timed on this GPU, scripts/ref_kernel_times.py); uploads and downloads lie outside
-static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
-static float g_last_ms = -1.f;
-#define RG_TRY(stmt) try { \
-        if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); } \
-        cudaEventRecord(g_ev0); \
-        stmt; \
-        cudaEventRecord(g_ev1); cudaEventSynchronize(g_ev1); cudaEventElapsedTime(&g_last_ms, g_ev0, g_ev1); \
-    } catch (std::exception const& e) { fprintf(stderr, "refgpu: %s\n", e.what()); return -1; }
 extern "C" float refgpu_last_kernel_ms() { return g_last_ms; }
-
-namespace {
-
-template <typename T>
-struct dbuf {
-    T* p = nullptr;
-    size_t n = 0;
-    explicit dbuf(size_t n_) : n(n_) { if (cudaMalloc(&p, (n ? n : 1) * sizeof(T)) != cudaSuccess) p = nullptr; }
-    dbuf(const T* host, size_t n_) : dbuf(n_) { if (p && n && host) cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice); }
-    ~dbuf() { if (p) cudaFree(p); }
-    int down(T* host) const { return static_cast<int>(cudaMemcpy(host, p, n * sizeof(T), cudaMemcpyDeviceToHost)); }
-    dbuf(dbuf const&) = delete;
-    dbuf& operator=(dbuf const&) = delete;
-};
-
-// linear-memory texture object, built as cuda::texture<T>(vector) builds it (cuda_wrapper/texture.hpp:33-46)
-template <typename T>
-struct lintex {
-    cudaTextureObject_t t = 0;
-    lintex(const T* dev, size_t n)
-    {
-        cudaResourceDesc rd = {};
-        rd.resType = cudaResourceTypeLinear;
-        rd.res.linear.devPtr = const_cast<T*>(dev);
-        rd.res.linear.desc = cudaCreateChannelDesc<T>();
-        rd.res.linear.sizeInBytes = n * sizeof(T);
-        cudaTextureDesc td = {};
-        td.readMode = cudaReadModeElementType;
-        cudaCreateTextureObject(&t, &rd, &td, nullptr);
-    }
-    ~lintex() { if (t) cudaDestroyTextureObject(t); }
-};
-
-template <typename V>
-V vec3(const float* v) { V r; for (int d = 0; d < 3; ++d) r[d] = v[d]; return r; }
-
-} // namespace
 
 extern "C" {
 
@@ -653,4 +605,66 @@ extern "C" int refgpu_correlate(int kind, const float* first4, const float* seco
     if (kind == 1) return reduce_correlation<observables::dynamics::mean_quartic_displacement<3, float>>(first4, second4, nparticle, out);
     if (kind == 2) return reduce_correlation<observables::dynamics::velocity_autocorrelation<3, float>>(first4, second4, nparticle, out);
     return reduce_correlation<observables::dynamics::mean_square_displacement<3, float>>(first4, second4, nparticle, out);
+}
+
+namespace {
+
+// reduce(&*unordered.begin(), &*unordered.end(), acc)  (mdsim/gpu/particle_group.hpp:133-247 through
+// algorithm/gpu/reduce.hpp:60-104): the reduction kernel over the particle indices of the group with the default
+// 16 x 1024 execution configuration, block results merged on the host in block order
+template <typename acc_type>
+int reduce_group(const unsigned int* d_group, size_t count, acc_type const& acc, acc_type& total)
+{
+    unsigned const blocks = 16, threads = 1024;
+    dbuf<acc_type> d_block(blocks);
+    if (!d_block.p) return static_cast<int>(cudaErrorMemoryAllocation);
+    auto& kernel = reduction_kernel<acc_type>::kernel;
+    RG_TRY(
+        kernel.reduce.configure(dim3(blocks), dim3(threads));
+        kernel.reduce(d_group, static_cast<std::ptrdiff_t>(count), d_block.p, acc);
+    )
+    RG_CHECK(cudaDeviceSynchronize());
+    std::vector<char> raw_bytes(blocks * sizeof(acc_type));
+    RG_CHECK(cudaMemcpy(raw_bytes.data(), d_block.p, raw_bytes.size(), cudaMemcpyDeviceToHost));
+    acc_type const* h = reinterpret_cast<acc_type const*>(raw_bytes.data());
+    total = acc;
+    for (unsigned i = 0; i < blocks; ++i) total(h[i]);
+    return 0;
+}
+
+} // namespace
+
+// observables::gpu::thermodynamics (thermodynamics.cpp:64-200) for the group of all particles: the accumulators of
+// observables/gpu/thermodynamics_kernel.{hpp,cu} — kinetic_energy, velocity_of_centre_of_mass, potential_energy, virial —
+// over velocity (float4[A], mass in w), potential energy (float[A]) and the stress tensor (float[6 A], stride A).
+// out = (sum m v^2, sum m v_x, sum m v_y, sum m v_z, sum m, sum en_pot, sum of the virial trace)
+extern "C" int refgpu_thermodynamics(const float* velocity4, const float* en_pot, const float* stress, size_t array_size,
+                                     size_t nparticle, double out[7])
+{
+    using namespace observables::gpu;
+    dbuf<float4> d_vel(reinterpret_cast<const float4*>(velocity4), array_size);
+    dbuf<float> d_en(en_pot, array_size), d_st(stress, 6 * array_size);
+    std::vector<unsigned int> h_group(nparticle);
+    for (size_t i = 0; i < nparticle; ++i) h_group[i] = static_cast<unsigned int>(i);
+    dbuf<unsigned int> d_group(h_group.data(), nparticle);
+    if (!d_vel.p || !d_en.p || !d_st.p || !d_group.p) return static_cast<int>(cudaErrorMemoryAllocation);
+    lintex<float4> t_v(d_vel.p, array_size);
+    lintex<float> t_en(d_en.p, array_size), t_st(d_st.p, 6 * array_size);
+    int rc;
+    kinetic_energy<3, dsfloat> ekin(t_v.t);
+    if ((rc = reduce_group(d_group.p, nparticle, kinetic_energy<3, dsfloat>(t_v.t), ekin))) return rc;
+    out[0] = 2 * ekin();
+    velocity_of_centre_of_mass<3, dsfloat> vcm(t_v.t);
+    if ((rc = reduce_group(d_group.p, nparticle, velocity_of_centre_of_mass<3, dsfloat>(t_v.t), vcm))) return rc;
+    fixed_vector<double, 3> mv;
+    double m;
+    std::tie(mv, m) = vcm();
+    out[1] = mv[0]; out[2] = mv[1]; out[3] = mv[2]; out[4] = m;
+    potential_energy<dsfloat> epot(t_en.t);
+    if ((rc = reduce_group(d_group.p, nparticle, potential_energy<dsfloat>(t_en.t), epot))) return rc;
+    out[5] = epot();
+    virial<3, dsfloat> vir(t_st.t, static_cast<unsigned int>(array_size));
+    if ((rc = reduce_group(d_group.p, nparticle, virial<3, dsfloat>(t_st.t, static_cast<unsigned int>(array_size)), vir))) return rc;
+    out[6] = vir();
+    return 0;
 }

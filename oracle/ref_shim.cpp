@@ -9,7 +9,11 @@
 #include <halmd/mdsim/gpu/potentials/pair/lennard_jones_kernel.hpp>
 #include <halmd/mdsim/positions/lattice_primitive.hpp>
 #include <halmd/numeric/accumulator.hpp>
+#include <halmd/algorithm/host/pick_lattice_points.hpp>
+#include <iterator>
+#include <map>
 #include <tuple>
+#include <vector>
 
 using namespace halmd;
 
@@ -59,6 +63,40 @@ void ref_accumulate(const double* x, unsigned n1, unsigned n2, double* out)
     for (unsigned i = n1; i < n1 + n2; ++i) b(x[i]);
     a(b);
     out[0] = static_cast<double>(count(a)); out[1] = mean(a); out[2] = variance(a);
+}
+
+
+// observables::utility::wavevector<3> (observables/utility/wavevector.cpp:40-123): the reference's
+// pick_lattice_points_from_shell (algorithm/host/pick_lattice_points.hpp:62-160) called with the arguments and the
+// multimap the constructor uses; vectors grouped by wavenumber in equal_range order, empty shells kept as empty ranges.
+int ref_wavevector_pick(const double* wavenumber, unsigned nwavenumber, const double box_length[3], double tolerance,
+                        unsigned max_count, const unsigned* filter, double* vectors_out, unsigned capacity,
+                        unsigned* shell_offsets_out)
+{
+    typedef fixed_vector<double, 3> vector_type;
+    typedef fixed_vector<unsigned int, 3> filter_type;
+    std::vector<double> q(wavenumber, wavenumber + nwavenumber);
+    vector_type L;
+    filter_type f(1);
+    for (int d = 0; d < 3; ++d) { L[d] = box_length[d]; if (filter) f[d] = filter[d]; }
+    auto first = q.begin();
+    auto last = q.end();
+    std::multimap<decltype(first), vector_type> wavevector_map;
+    algorithm::host::pick_lattice_points_from_shell(
+        first, last, std::inserter(wavevector_map, wavevector_map.end()), element_div(vector_type(2 * M_PI), L), tolerance,
+        max_count, f);
+    unsigned total = 0;
+    for (auto q_it = q.begin(); q_it != q.end(); ++q_it) {
+        shell_offsets_out[q_it - q.begin()] = total;
+        auto range = wavevector_map.equal_range(q_it);
+        for (auto it = range.first; it != range.second; ++it) {
+            if (total >= capacity) return -1;
+            for (int d = 0; d < 3; ++d) vectors_out[3 * total + d] = it->second[d];
+            ++total;
+        }
+    }
+    shell_offsets_out[nwavenumber] = total;
+    return 0;
 }
 
 }

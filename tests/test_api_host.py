@@ -70,3 +70,53 @@ def test_potential_errors(mdsim):
     from halmd_b200.api import HxError
     with pytest.raises(HxError):
         lj.modify("hard_core", radius=3.0).truncate("shifted", cutoff=2.5)     # core radius beyond the cutoff
+
+
+# ---- a16: wavevector shells (host logic of the C ABI, no device work) ---------------------------------------------------
+def _pick(hx, L, q, tol, max_count, filt):
+    nw = len(q)
+    cap = nw * max_count
+    vec = np.zeros((cap, 3))
+    offs = (C.c_uint * (nw + 1))()
+    f = None if filt is None else (C.c_uint * 3)(*filt)
+    hx.check(hx.lib.hx_wavevector_pick((C.c_double * nw)(*q), nw, hx.d3(L), float(tol), int(max_count), f,
+                                       vec.ctypes.data_as(hx.D3), cap, offs), "hx_wavevector_pick")
+    return vec[:offs[nw]], list(offs)
+
+
+def test_wavevector_shells_equal_the_reference_golden(hx):
+    """hx_wavevector_pick against tests/golden/wavevectors.json — shells picked by the reference's own
+    pick_lattice_points_from_shell (halmd/algorithm/host/pick_lattice_points.hpp:62-160, compiled in place and called as
+    observables/utility/wavevector.cpp:40-123 does; scripts/make_golden_wavevectors.py): same vectors, bit for bit, in the
+    same order, same shell boundaries — cubic and cuboid boxes, semilog grid, filters, a tolerance that empties shells."""
+    g = support.golden("wavevectors.json")
+    assert len(g["cases"]) >= 6
+    for case in g["cases"]:
+        vec, offs = _pick(hx, case["L"], case["wavenumbers"], case["tol"], case["max_count"], case["filter"])
+        want = np.array([[float.fromhex(x) for x in v] for v in case["vectors"]]).reshape(-1, 3)
+        assert offs == case["shell_offsets"], case["name"]
+        assert vec.tobytes() == want.tobytes(), case["name"]
+
+
+def test_wavevector_shells_equal_the_compiled_reference(hx, ref):
+    """The same comparison against oracle/_ref/libhalmd_ref.so directly, on randomised boxes and grids."""
+    ref.ref_wavevector_pick.restype = C.c_int
+    rng = np.random.default_rng(17)
+    for _ in range(12):
+        L = list(rng.uniform(8.0, 40.0, 3)) if rng.random() < 0.5 else [float(rng.uniform(8.0, 40.0))] * 3
+        q = sorted(rng.uniform(0.2, 9.0, int(rng.integers(1, 9))))
+        tol, max_count = float(rng.choice([0.005, 0.01, 0.05])), int(rng.integers(1, 10))
+        filt = None if rng.random() < 0.6 else [int(x) for x in rng.integers(0, 2, 3)]
+        nw, cap = len(q), len(q) * max_count
+        rvec = np.zeros((cap, 3))
+        roffs = (C.c_uint * (nw + 1))()
+        f = None if filt is None else (C.c_uint * 3)(*filt)
+        assert ref.ref_wavevector_pick((C.c_double * nw)(*q), nw, hx.d3(L), C.c_double(tol), max_count, f,
+                                       rvec.ctypes.data_as(hx.D3), cap, roffs) == 0
+        if roffs[nw] == 0:
+            assert hx.lib.hx_wavevector_pick((C.c_double * nw)(*q), nw, hx.d3(L), tol, max_count, f,
+                                             rvec.ctypes.data_as(hx.D3), cap, roffs) < 0      # wavevector.cpp:84-87: logic_error
+            continue
+        vec, offs = _pick(hx, L, q, tol, max_count, filt)
+        assert offs == list(roffs)
+        assert vec.tobytes() == rvec[:roffs[nw]].tobytes()

@@ -700,7 +700,7 @@ def test_thermodynamics(hx, oracle, dev):
     en = rng.normal(size=A).astype(np.float32)
     st = rng.normal(size=6 * A).astype(np.float32)
     d_v, d_e, d_s = dev.up(v), dev.up(en), dev.up(st)
-    d_out = dev.zeros(8, np.float64)
+    d_out = dev.zeros(hx.THERMO_DOUBLES, np.float64)
     hx.check(hx.lib.hx_thermodynamics(dev.p(d_v), dev.p(d_e), dev.p(d_s), A, n, dev.p(d_out), dev.stream))
     out = dev.down(d_out)
     o = np.zeros(8)
