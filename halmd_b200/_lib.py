@@ -46,6 +46,32 @@ class ShellRows(C.Structure):
     _fields_ = [("rows_dev", C.c_void_p), ("ends_dev", C.c_void_p), ("pitch", C.c_uint), ("delta", C.c_float * NSHELL)]
 
 
+DD_MAX_RANKS, DD_IPC_HANDLE_BYTES = 32, 64
+
+
+class Rand48(C.Structure):
+    _fields_ = [("blocks", C.c_uint), ("threads", C.c_uint), ("a", C.c_uint16 * 3), ("c", C.c_uint16 * 3)]
+
+
+class DdSteps(C.Structure):
+    """hx_dd_steps (include/halmd_b200.h): everything one chunk of decomposed MD steps needs, device pointers as integers."""
+    _fields_ = [
+        ("position_dev", C.c_void_p * 2), ("current", C.c_int),
+        ("image_dev", C.c_void_p), ("velocity_dev", C.c_void_p), ("force_dev", C.c_void_p), ("r0_dev", C.c_void_p),
+        ("n_own", C.c_size_t), ("n_ghost", C.c_size_t), ("array_size", C.c_size_t),
+        ("timestep", C.c_float), ("box_length", C.c_float * 3),
+        ("nranks", C.c_int), ("rank", C.c_int),
+        ("send_index_dev", C.c_void_p * 2), ("send_count", C.c_size_t * 2),
+        ("peer_ghost_dev", (C.c_void_p * 2) * 2),
+        ("peer_inbox_dev", C.c_void_p), ("inbox_dev", C.c_void_p), ("timeout_cycles", C.c_longlong),
+        ("ctl_dev", C.c_void_p), ("skin_half", C.c_float), ("step_base", C.c_uint64), ("pending_finalize", C.c_int),
+        ("potential", C.POINTER(LjParams)), ("shells", C.POINTER(ShellRows)), ("g_neighbour_dev", C.c_void_p),
+        ("size", C.c_uint), ("stride", C.c_size_t),
+        ("rng", C.POINTER(Rand48)), ("rng_state_dev", C.c_void_p), ("andersen_scratch_dev", C.c_void_p),
+        ("andersen_scratch_bytes", C.c_size_t), ("sqrt_temperature", C.c_float), ("coll_prob", C.c_float),
+    ]
+
+
 MAX_WALLS, MAX_WALL_SPECIES = 8, 4
 
 
@@ -61,10 +87,6 @@ class PlanarWall(C.Structure):
         ("epsilon", C.c_float * (MAX_WALL_SPECIES * MAX_WALLS)), ("sigma", C.c_float * (MAX_WALL_SPECIES * MAX_WALLS)),
         ("wetting", C.c_float * (MAX_WALL_SPECIES * MAX_WALLS)), ("cutoff", C.c_float * (MAX_WALL_SPECIES * MAX_WALLS)),
     ]
-
-
-class Rand48(C.Structure):
-    _fields_ = [("blocks", C.c_uint), ("threads", C.c_uint), ("a", C.c_uint16 * 3), ("c", C.c_uint16 * 3)]
 
 
 if not os.path.exists(LIB_PATH):
@@ -154,6 +176,12 @@ _protos = {
     "hx_dd_permute": (C.c_int, [P, SZ, SZ, P, P, P, P, P, P, P, P, P]),
     "hx_gather_float4": (C.c_int, [P, P, SZ, P, P, P]),
     "hx_gather_u32": (C.c_int, [P, P, SZ, P, P]),
+    "hx_dd_alloc": (C.c_int, [SZ, C.POINTER(C.c_void_p)]),
+    "hx_dd_free": (C.c_int, [P]),
+    "hx_dd_ipc_export": (C.c_int, [P, C.c_char_p]),
+    "hx_dd_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "hx_dd_ipc_close": (C.c_int, [P]),
+    "hx_dd_enqueue_steps": (C.c_int, [C.POINTER(DdSteps), C.c_uint, P]),
 }
 
 KERNEL_SYMBOLS = tuple(_protos)

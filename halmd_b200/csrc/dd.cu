@@ -6,6 +6,7 @@
 // are expressed as small integer keys that the caller feeds to the stable radix sort (hx_sort_pairs_stable_u32), so
 // that migrants and ghosts keep their relative memory order.  Host orchestration: halmd_b200/decomposition.py.
 #include "common.cuh"
+#include <cstring>
 
 namespace hx {
 
@@ -90,6 +91,55 @@ __global__ void k_gather_u32(const unsigned* __restrict__ src, const unsigned* _
     if (i < n) dst[i] = __ldg(&src[index[i]]);
 }
 
+
+// ---- per-step halo exchange and rebuild vote over peer memory ---------------------------------------------------------
+// The ranks of one node map each other's position buffers and inboxes (CUDA IPC).  After the integration kernel of a
+// step, k_gather_f4 stores the new positions of this rank's boundary particles straight into the ghost slots of the
+// neighbours' position buffers (NVLink stores, no staging, no host), k_dd_signal publishes {step, local maximum squared
+// displacement} in every other rank's inbox, and k_dd_wait — the only point where a rank waits for others — spins until
+// all inbox entries carry this step, folds the global maximum into the control block (the rebuild vote) and lets the
+// force kernel go.  Positions are double-buffered: step k lives in buffer k % 2, so a neighbour that is one kernel ahead
+// writes the ghosts of step k + 1 while this rank's force kernel still reads those of step k.
+__global__ void k_dd_signal(const unsigned* __restrict__ ctl, unsigned long long* const* __restrict__ peer_inbox, int nranks, int rank,
+                            unsigned step)
+{
+    if (ctl[CTL_HALTED]) return;
+    int const r = threadIdx.x;
+    if (r >= nranks || r == rank) return;
+    // the pushes of this step (earlier kernels of the stream) are performed before the flag becomes visible
+    __threadfence_system();
+    unsigned long long const word = (static_cast<unsigned long long>(step) << 32) | ctl[CTL_MAX_RR];
+    // two inbox rows, used alternately: a peer that is a step ahead writes the other row, and cannot get two steps
+    // ahead without this rank's next signal
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(peer_inbox[r] + (step & 1u) * HX_DD_MAX_RANKS + rank), "l"(word) : "memory");
+}
+
+__global__ void k_dd_wait(unsigned* __restrict__ ctl, const unsigned long long* __restrict__ inbox, int nranks, int rank, unsigned step,
+                          long long timeout_cycles)
+{
+    if (ctl[CTL_HALTED]) return;
+    int const r = threadIdx.x;
+    unsigned max_rr = 0;
+    bool timed_out = false;
+    if (r < nranks && r != rank) {
+        long long const t0 = clock64();
+        for (;;) {
+            unsigned long long word;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(inbox + (step & 1u) * HX_DD_MAX_RANKS + r) : "memory");
+            if (static_cast<unsigned>(word >> 32) == step) { max_rr = static_cast<unsigned>(word); break; }
+            if (clock64() - t0 > timeout_cycles) { timed_out = true; break; }
+            __nanosleep(200);
+        }
+    }
+    if (timed_out) {
+        // a peer never arrived: stop the chunk instead of hanging the device; the host reports ctl[3]
+        atomicExch(&ctl[CTL_RESERVED], 0xDEADu);
+        atomicExch(&ctl[CTL_HALTED], 1u);
+        return;
+    }
+    if (max_rr) atomicMax(&ctl[CTL_MAX_RR], max_rr);
+}
+
 } // namespace hx
 
 using namespace hx;
@@ -166,6 +216,104 @@ int hx_gather_u32(const uint32_t* src_dev, const uint32_t* index_dev, size_t n, 
     if (n == 0) return HX_OK;
     k_gather_u32<<<div_up(n, 256), 256, 0, as_stream(stream)>>>(src_dev, index_dev, static_cast<unsigned>(n), dst_dev);
     return check_launch("k_gather_u32");
+}
+
+
+// ---- device memory that other processes of the node can map (cudaMalloc'ed, not sub-allocated) ---------------------
+int hx_dd_alloc(size_t bytes, void** out_dev)
+{
+    if (!out_dev || bytes == 0) { set_error("hx_dd_alloc: invalid argument"); return HX_E_INVALID; }
+    cudaError_t err = cudaMalloc(out_dev, bytes);
+    if (err == cudaSuccess) err = cudaMemset(*out_dev, 0, bytes);
+    if (err != cudaSuccess) { set_error("hx_dd_alloc: %s", cudaGetErrorString(err)); return static_cast<int>(err); }
+    return HX_OK;
+}
+
+int hx_dd_free(void* dev)
+{
+    cudaError_t err = cudaFree(dev);
+    if (err != cudaSuccess) { set_error("hx_dd_free: %s", cudaGetErrorString(err)); return static_cast<int>(err); }
+    return HX_OK;
+}
+
+int hx_dd_ipc_export(void* dev, unsigned char handle_out[HX_DD_IPC_HANDLE_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == HX_DD_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t err = cudaIpcGetMemHandle(&h, dev);
+    if (err != cudaSuccess) { set_error("hx_dd_ipc_export: %s", cudaGetErrorString(err)); return static_cast<int>(err); }
+    memcpy(handle_out, &h, sizeof(h));
+    return HX_OK;
+}
+
+int hx_dd_ipc_open(const unsigned char handle[HX_DD_IPC_HANDLE_BYTES], void** out_dev)
+{
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    cudaError_t err = cudaIpcOpenMemHandle(out_dev, h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) { set_error("hx_dd_ipc_open: %s", cudaGetErrorString(err)); return static_cast<int>(err); }
+    return HX_OK;
+}
+
+int hx_dd_ipc_close(void* dev)
+{
+    cudaError_t err = cudaIpcCloseMemHandle(dev);
+    if (err != cudaSuccess) { set_error("hx_dd_ipc_close: %s", cudaGetErrorString(err)); return static_cast<int>(err); }
+    return HX_OK;
+}
+
+// One chunk of speculatively enqueued MD steps of the decomposed loop (see the kernels above); nothing here touches
+// the host between steps.  Returns after enqueueing; the caller reads the control block (steps completed, halted).
+int hx_dd_enqueue_steps(const hx_dd_steps* a, unsigned chunk, void* stream)
+{
+    if (!a || !a->position_dev[0] || !a->position_dev[1] || !a->image_dev || !a->velocity_dev || !a->force_dev || !a->r0_dev
+        || !a->ctl_dev || !a->potential || a->nranks < 1 || a->nranks > HX_DD_MAX_RANKS || a->rank < 0 || a->rank >= a->nranks
+        || (a->current != 0 && a->current != 1) || (!a->shells && !a->g_neighbour_dev)
+        || (a->nranks > 1 && (!a->inbox_dev || !a->peer_inbox_dev))) {
+        set_error("hx_dd_enqueue_steps: invalid argument");
+        return HX_E_INVALID;
+    }
+    cudaStream_t st = as_stream(stream);
+    int cur = a->current;
+    bool const andersen = a->rng != nullptr;
+    size_t const ntot = a->n_own + a->n_ghost;
+    for (unsigned k = 0; k < chunk; ++k) {
+        unsigned const step = static_cast<unsigned>(a->step_base + k + 1);
+        hx_float4* const pin = a->position_dev[cur];
+        hx_float4* const pout = a->position_dev[cur ^ 1];
+        bool const fin = !andersen && (a->pending_finalize || k > 0);
+        int rc = verlet_launch(fin, true, pin, a->image_dev, a->velocity_dev, a->force_dev, a->n_own, a->array_size, a->timestep,
+                               a->box_length, a->r0_dev, a->ctl_dev, stream, a->n_own, pout);
+        if (rc) return rc;
+        if (a->nranks > 1) {
+            for (int dir = 0; dir < 2; ++dir) {
+                if (a->send_count[dir] == 0) continue;
+                rc = hx_gather_float4(pout, a->send_index_dev[dir], a->send_count[dir], a->peer_ghost_dev[dir][cur ^ 1], a->ctl_dev, stream);
+                if (rc) return rc;
+            }
+            k_dd_signal<<<1, HX_DD_MAX_RANKS, 0, st>>>(a->ctl_dev, a->peer_inbox_dev, a->nranks, a->rank, step);
+            if ((rc = check_launch("k_dd_signal"))) return rc;
+            k_dd_wait<<<1, HX_DD_MAX_RANKS, 0, st>>>(a->ctl_dev, a->inbox_dev, a->nranks, a->rank, step, a->timeout_cycles);
+            if ((rc = check_launch("k_dd_wait"))) return rc;
+        }
+        int const flags = HX_FORCE_POSITIONS_REDUCED;
+        if (a->shells) {
+            rc = hx_pair_force_shells(a->potential, pout, pout, a->shells, a->r0_dev, a->n_own, a->box_length, flags, 1, a->force_dev,
+                                      a->ctl_dev, a->skin_half, stream);
+        } else {
+            rc = hx_pair_force2(a->potential, pout, pout, ntot, a->g_neighbour_dev, a->size, a->stride, HX_LAYOUT_ROW | flags, a->n_own,
+                                a->box_length, 1, 0.5f, a->force_dev, nullptr, nullptr, a->array_size, a->ctl_dev, a->skin_half, stream);
+        }
+        if (rc) return rc;
+        if (andersen) {
+            rc = hx_andersen_finalize2(a->velocity_dev, a->force_dev, a->n_own, a->array_size, a->timestep, a->sqrt_temperature,
+                                       a->coll_prob, a->rng, a->rng_state_dev, a->andersen_scratch_dev, a->andersen_scratch_bytes,
+                                       a->ctl_dev, stream);
+            if (rc) return rc;
+        }
+        cur ^= 1;
+    }
+    return HX_OK;
 }
 
 } // extern "C"

@@ -71,8 +71,11 @@ __device__ __forceinline__ float4 ld_ordered(const float4* p)
     return v;
 }
 
+// pos_out: where the new positions go — pos itself in the single-GPU loop; the other buffer of the double-buffered
+// positions in the decomposed loop, whose ghost slots the neighbour ranks fill over NVLink while this rank's force kernel
+// may still read the old buffer (dd.cu).  All loads of pos precede the stores, so the two may alias.
 template <bool FINALIZE, bool INTEGRATE>
-__global__ void __launch_bounds__(128) k_verlet(float4* __restrict__ pos, float4* __restrict__ image,
+__global__ void __launch_bounds__(128) k_verlet(const float4* pos, float4* pos_out, float4* __restrict__ image,
                                                float4* __restrict__ vel, const float4* __restrict__ force,
                                                unsigned n, unsigned nproc, unsigned A, float dt, vec3 L, vec3 invL,
                                                const float4* __restrict__ r0, unsigned* __restrict__ ctl)
@@ -107,8 +110,8 @@ __global__ void __launch_bounds__(128) k_verlet(float4* __restrict__ pos, float4
             float ix = drift_wrap(rx, v.x, dt, L.x);
             float iy = drift_wrap(ry, v.y, dt, L.y);
             float iz = drift_wrap(rz, v.z, dt, L.z);
-            pos[i] = make_float4(rx.hi, ry.hi, rz.hi, ph.w);
-            pos[i + A] = make_float4(rx.lo, ry.lo, rz.lo, 0.f);
+            pos_out[i] = make_float4(rx.hi, ry.hi, rz.hi, ph.w);
+            pos_out[i + A] = make_float4(rx.lo, ry.lo, rz.lo, 0.f);
             if (!(ix == 0.f && iy == 0.f && iz == 0.f)) {
                 float4 im = image[i];
                 image[i] = make_float4(__fadd_rn(ix, im.x), __fadd_rn(iy, im.y), __fadd_rn(iz, im.z), 0.f);
@@ -445,9 +448,13 @@ int hx_state_init(hx_float4* position_dev, hx_float4* velocity_dev, hx_float4* i
     return check_launch("k_state_init");
 }
 
-static int verlet_launch(bool fin, bool integ, hx_float4* pos, hx_float4* image, hx_float4* vel,
-                         const hx_float4* force, size_t n, size_t A, float dt, const float L[3],
-                         const hx_float4* r0, uint32_t* ctl, void* stream, size_t nproc_arg = ~size_t(0))
+} // extern "C"
+
+namespace hx {
+
+int verlet_launch(bool fin, bool integ, hx_float4* pos, hx_float4* image, hx_float4* vel,
+                  const hx_float4* force, size_t n, size_t A, float dt, const float L[3],
+                  const hx_float4* r0, uint32_t* ctl, void* stream, size_t nproc_arg, hx_float4* pos_out_arg)
 {
     size_t const nproc = nproc_arg == ~size_t(0) ? A : nproc_arg;
     if (!vel || !force || A == 0 || A >= 0x7FFFFFFFull || n > A || nproc > A || (integ && (!pos || !image || !L))
@@ -463,16 +470,21 @@ static int verlet_launch(bool fin, bool integ, hx_float4* pos, hx_float4* image,
     dim3 grid(div_up(nproc > 0 ? nproc : 1, 128)), block(128);
     cudaStream_t st = as_stream(stream);
     float4* p = reinterpret_cast<float4*>(pos);
+    float4* po = reinterpret_cast<float4*>(pos_out_arg ? pos_out_arg : pos);
     float4* im = reinterpret_cast<float4*>(image);
     float4* v = reinterpret_cast<float4*>(vel);
     const float4* f = reinterpret_cast<const float4*>(force);
     const float4* q = reinterpret_cast<const float4*>(r0);
     unsigned nn = static_cast<unsigned>(n), AA = static_cast<unsigned>(A), np = static_cast<unsigned>(nproc);
-    if (fin && integ) launch_pdl(k_verlet<true, true>, grid, block, 0, st, p, im, v, f, nn, np, AA, dt, Lv, iLv, q, ctl);
-    else if (integ) launch_pdl(k_verlet<false, true>, grid, block, 0, st, p, im, v, f, nn, np, AA, dt, Lv, iLv, q, ctl);
-    else launch_pdl(k_verlet<true, false>, grid, block, 0, st, p, im, v, f, nn, np, AA, dt, Lv, iLv, q, ctl);
+    if (fin && integ) launch_pdl(k_verlet<true, true>, grid, block, 0, st, p, po, im, v, f, nn, np, AA, dt, Lv, iLv, q, ctl);
+    else if (integ) launch_pdl(k_verlet<false, true>, grid, block, 0, st, p, po, im, v, f, nn, np, AA, dt, Lv, iLv, q, ctl);
+    else launch_pdl(k_verlet<true, false>, grid, block, 0, st, p, po, im, v, f, nn, np, AA, dt, Lv, iLv, q, ctl);
     return check_launch("k_verlet");
 }
+
+} // namespace hx
+
+extern "C" {
 
 int hx_verlet_integrate(hx_float4* position_dev, hx_float4* image_dev, hx_float4* velocity_dev,
                         const hx_float4* force_dev, size_t array_size, float timestep, const float box_length[3],

@@ -7,10 +7,13 @@ within r_c + skin of its faces.  Particle coordinates stay global, so the kernel
 the periodic wrap, and binning uses the *global* cell grid of the single-GPU run: every owned particle therefore gets
 exactly the neighbour set the single-GPU code would give it.
 
-Per MD step:   fused finalize/integrate (owned) -> pack + exchange ghost positions -> all-reduce(max) of the
-               displacement word -> guarded pair force (owned rows, ghost partners)
+Per MD step (hx_dd_enqueue_steps, csrc/dd.cu — no host code and no library collective between the kernels of a step):
+               fused finalize/integrate of the owned particles into the other position buffer -> the boundary
+               particles' new positions stored straight into the neighbours' ghost slots (peer memory over NVLink) ->
+               signal {step, local displacement maximum} to every rank's inbox -> wait for all inboxes, global maximum
+               into the control block (the rebuild vote) -> guarded pair force (owned rows, ghost partners)
 Per list update (when the device-side displacement test trips): migrate leavers to the neighbouring ranks, Hilbert
-order, select + exchange ghosts, bin, build lists, reset displacement origin.
+order, select + exchange ghosts, bin, build lists, reset displacement origin — host-orchestrated, torch.distributed.
 
 Three layers, so that the host logic is testable without a GPU:
   SlabDecomposition  geometry and ownership arithmetic (pure numpy restatement of csrc/dd.cu, used by the tests)
@@ -167,9 +170,29 @@ class Exchange:
         if self.nranks > 1:
             self.dist.barrier(group=self.group)
 
+    def allgather_object(self, obj):
+        """[obj of rank 0, ..., obj of rank P-1] (small host objects: IPC handles, buffer indices)."""
+        if self.nranks == 1:
+            return [obj]
+        out = [None] * self.nranks
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
 
 def _round_up(n, m):
     return ((int(n) + m - 1) // m) * m
+
+
+class _DeviceArray:
+    """A device allocation of the C library exposed through the CUDA array interface (so torch can view it)."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 2}
+        self.owner = owner
+
+
+def _device_view(torch, ptr, shape, typestr, owner):
+    return torch.as_tensor(_DeviceArray(ptr, shape, typestr, owner), device="cuda")
 
 
 class DecomposedSystem:
@@ -250,7 +273,18 @@ class DecomposedSystem:
         f32, i32 = torch.float32, torch.int32
         z = lambda *shape, dtype=f32: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
         cap = self.cap
-        self.pos, self.pos_b = z(2 * cap, 4), z(2 * cap, 4)
+        # positions: two buffers allocated by the library (plain cudaMalloc: exportable to the other ranks), used
+        # alternately by the step loop; `cur` is the one holding the current positions
+        self._pos_ptr, self._pos_t, self.cur = [], [], 0
+        for _ in range(2):
+            ptr = C.c_void_p()
+            hx.check(self.lib.hx_dd_alloc(2 * cap * 16, C.byref(ptr)), "hx_dd_alloc")
+            self._pos_ptr.append(ptr.value)
+            self._pos_t.append(_device_view(torch, ptr.value, (2 * cap, 4), "<f4", self))
+        inbox = C.c_void_p()
+        hx.check(self.lib.hx_dd_alloc(2 * hx.DD_MAX_RANKS * 8, C.byref(inbox)), "hx_dd_alloc")
+        self._inbox_ptr = inbox.value
+        self._map_peers()
         self.vel, self.vel_b = z(2 * cap, 4), z(2 * cap, 4)
         self.image, self.image_b = z(cap, 4), z(cap, 4)
         self.force = z(cap, 4)
@@ -300,11 +334,73 @@ class DecomposedSystem:
             self.rng_state = torch.zeros(3 * 32 * 256, dtype=torch.int16, device=dev)
             hx.check(self.lib.hx_rand48_seed(C.byref(self.rng), 32, 256, int(seed) + 7919 * rank, self._p(self.rng_state), self.st))
             self.set_temperature(temperature, rate)
+        self.use_shells = True
+        self.shells, self.shell_rows, self.shell_ends = None, None, None
+        self.timeout_cycles = int(20e9)            # ~10 s of SM clock: a rank that never arrives stops the chunk
         self.lists_valid = False
         self.force_valid = False
         self.pending_finalize = False
         self.last_interval, self.since_update = 16, 0
         self.min_chunk, self.max_chunk = 2, 64
+
+    # ---- position buffers and peer memory --------------------------------------------------------------------
+    @property
+    def pos(self):
+        return self._pos_t[self.cur]
+
+    @property
+    def pos_b(self):
+        return self._pos_t[self.cur ^ 1]
+
+    def _map_peers(self):
+        """Exchange the IPC handles of the position buffers and the inbox; map those of the other ranks."""
+        hx, torch = self.hx, self.torch
+        self._peer_pos = {self.rank: list(self._pos_ptr)}
+        self._peer_inbox = {self.rank: self._inbox_ptr}
+        if self.nranks > 1:
+            mine = []
+            for ptr in self._pos_ptr + [self._inbox_ptr]:
+                h = C.create_string_buffer(hx.DD_IPC_HANDLE_BYTES)
+                hx.check(self.lib.hx_dd_ipc_export(C.c_void_p(ptr), h), "hx_dd_ipc_export")
+                mine.append(h.raw)
+            everyone = self.ex.allgather_object(mine)
+            needed = {self.dec.left, self.dec.right}
+            for r, handles in enumerate(everyone):
+                if r == self.rank:
+                    continue
+                opened = []
+                for k, raw in enumerate(handles):
+                    if k < 2 and r not in needed:      # positions of the two neighbours only; every rank's inbox
+                        opened.append(None)
+                        continue
+                    ptr = C.c_void_p()
+                    hx.check(self.lib.hx_dd_ipc_open(raw, C.byref(ptr)), "hx_dd_ipc_open")
+                    opened.append(ptr.value)
+                self._peer_pos[r] = opened[:2]
+                self._peer_inbox[r] = opened[2]
+        table = np.zeros(hx.DD_MAX_RANKS, dtype=np.uint64)
+        for r, ptr in self._peer_inbox.items():
+            table[r] = ptr
+        self.peer_inbox_table = torch.from_numpy(table.view(np.int64)).to(torch.device("cuda", torch.cuda.current_device()))
+        self.peer_flip = {"left": 0, "right": 0}
+        self.peer_offset = {"left": 0, "right": 0}
+
+    def close(self):
+        """Unmap the peers' buffers and free the exported ones (collective: every rank calls it)."""
+        if getattr(self, "_pos_ptr", None) is None:
+            return
+        self.torch.cuda.synchronize()
+        self.ex.barrier()
+        for r, ptrs in self._peer_pos.items():
+            if r != self.rank:
+                for ptr in list(ptrs) + [self._peer_inbox[r]]:
+                    if ptr:
+                        self.lib.hx_dd_ipc_close(C.c_void_p(ptr))
+        self.ex.barrier()
+        self._pos_t = None
+        for ptr in self._pos_ptr + [self._inbox_ptr]:
+            self.lib.hx_dd_free(C.c_void_p(ptr))
+        self._pos_ptr = None
 
     # ---- helpers ---------------------------------------------------------------------------------------------
     @staticmethod
@@ -344,7 +440,7 @@ class DecomposedSystem:
         self.hx.check(self.lib.hx_dd_permute(self._p(self.index), n, self.cap, self._p(self.pos), self._p(self.pos_b),
                                              self._p(self.vel), self._p(self.vel_b), self._p(self.image), self._p(self.image_b),
                                              self._p(self.id), self._p(self.id_b), self.st), "permute")
-        self.pos, self.pos_b = self.pos_b, self.pos
+        self.cur ^= 1
         self.vel, self.vel_b = self.vel_b, self.vel
         self.image, self.image_b = self.image_b, self.image
         self.id, self.id_b = self.id_b, self.id
@@ -486,12 +582,62 @@ class DecomposedSystem:
         self._build()
         hx.check(self.lib.hx_displacement_zero(self._p(self.pos), self._p(self.r0), self.n_own, self.st))
         hx.check(self.lib.hx_ctl_reset(self._p(self.ctl), self.st))
+        self._build_shells()
+        self._exchange_landing()
         self.lists_valid = True
         self.updates += 1
+
+    def _build_shells(self):
+        """Private shell-ordered rows of the owned particles for the pair-force kernel (hx_shell_rows_build)."""
+        hx, torch = self.hx, self.torch
+        self.shells = None
+        if not self.use_shells or self.n_own == 0:
+            return
+        hx.check(self.lib.hx_count_max(self._p(self.nl_count), self.n_own, self._p(self.counts), self.st), "count_max")
+        longest = int(self.counts[0].item())
+        self.stats["syncs"] += 1
+        pitch = (longest + 32) // 32 * 32
+        if pitch > 512:
+            return
+        words = int(self.lib.hx_shell_rows_words(self.own_cap, pitch))
+        if self.shell_rows is None or self.shell_rows.numel() < words:
+            self.shell_rows = torch.empty(words, dtype=torch.int32, device=self.vel.device)
+        if self.shell_ends is None:
+            self.shell_ends = torch.empty(self.own_cap * hx.NSHELL, dtype=torch.int16, device=self.vel.device)
+        sh = hx.ShellRows()
+        hx.check(self.lib.hx_shell_rows_plan(self.skin, C.byref(sh)))
+        sh.rows_dev, sh.ends_dev, sh.pitch = self.shell_rows.data_ptr(), self.shell_ends.data_ptr(), pitch
+        hx.check(self.lib.hx_shell_rows_build(C.byref(self.pot), self._p(self.nl), self.stride, self._p(self.nl_count), self._p(self.pos),
+                                              self._p(self.pos), self.n_own, self.Lf, C.byref(sh), self.st), "shell_rows")
+        self.shells = sh
+
+    def _exchange_landing(self):
+        """Tell the two neighbours where their ghost blocks land in this rank's position buffers (slot offset and
+        which of the two buffers is current): the step loop stores straight into those slots (peer memory)."""
+        if self.nranks == 1:
+            return
+        torch = self.torch
+        fr = self.n_ghost_from["right"]
+        dev = "cpu" if self.ex.stage else self.vel.device
+        to_left = torch.tensor([self.n_own + fr, self.cur], dtype=torch.int64, device=dev)    # for the sender of `from_left`
+        to_right = torch.tensor([self.n_own, self.cur], dtype=torch.int64, device=dev)        # for the sender of `from_right`
+        of_right, of_left = torch.zeros_like(to_left), torch.zeros_like(to_left)
+        self.ex.sendrecv(to_left, to_right, of_right, of_left)
+        # my leftward block is the left neighbour's `from_right` block: it told me (rightward message) where it lands
+        of_left, of_right = of_left.cpu().numpy(), of_right.cpu().numpy()
+        self.peer_offset = {"left": int(of_left[0]), "right": int(of_right[0])}
+        # relative orientation of my two buffers and each neighbour's, fixed until the next list update (every executed
+        # step switches the current buffer on all ranks alike)
+        self.peer_flip = {"left": int(of_left[1]) ^ self.cur, "right": int(of_right[1]) ^ self.cur}
 
     # ---- forces, integration ------------------------------------------------------------------------------------------
     def _force(self, aux=False, guarded=False):
         hx = self.hx
+        if not aux and self.shells is not None:
+            hx.check(self.lib.hx_pair_force_shells(C.byref(self.pot), self._p(self.pos), self._p(self.pos), C.byref(self.shells),
+                                                   self._p(self.r0), self.n_own, self.Lf, 0, 1, self._p(self.force),
+                                                   self._p(self.ctl) if guarded else None, self.skin_half, self.st), "pair_force_shells")
+            return
         hx.check(self.lib.hx_pair_force2(C.byref(self.pot), self._p(self.pos), self._p(self.pos), self.n_own + self.n_ghost,
                                          self._p(self.nl), self.size, self.stride, hx.LAYOUT_ROW | self.lanes_flag, self.n_own, self.Lf, 1, 0.5,
                                          self._p(self.force), self._p(self.en_pot) if aux else None,
@@ -529,9 +675,57 @@ class DecomposedSystem:
             self._verlet(True, False, False)
             self.pending_finalize = False
 
+    def _steps_descriptor(self):
+        """hx_dd_steps for the current state (device pointers, counts, where the pushes land)."""
+        hx = self.hx
+        a = hx.DdSteps()
+        a.position_dev[0], a.position_dev[1] = self._pos_ptr[0], self._pos_ptr[1]
+        a.current = self.cur
+        a.image_dev, a.velocity_dev, a.force_dev = self.image.data_ptr(), self.vel.data_ptr(), self.force.data_ptr()
+        a.r0_dev = self.r0.data_ptr()
+        a.n_own, a.n_ghost, a.array_size = self.n_own, self.n_ghost, self.cap
+        a.timestep = self.dt
+        for d in range(3):
+            a.box_length[d] = self.Lf[d]
+        a.nranks, a.rank = self.nranks, self.rank
+        if self.nranks > 1:
+            for k, dest in enumerate(("left", "right")):
+                peer = self.dec.left if dest == "left" else self.dec.right
+                idx = self.send_idx[dest]
+                a.send_index_dev[k] = idx.data_ptr() if idx.numel() else None
+                a.send_count[k] = idx.numel()
+                for b in range(2):
+                    # at every step all ranks write the buffer that is not their current one: my buffer b is in use when
+                    # the peer's buffer b ^ peer_flip is
+                    pb = b ^ self.peer_flip[dest]
+                    a.peer_ghost_dev[k][b] = self._peer_pos[peer][pb] + 16 * self.peer_offset[dest]
+            a.peer_inbox_dev = self.peer_inbox_table.data_ptr()
+            a.inbox_dev = self._inbox_ptr
+        a.timeout_cycles = self.timeout_cycles
+        a.ctl_dev = self.ctl.data_ptr()
+        a.skin_half = self.skin_half
+        a.step_base = self.step
+        a.pending_finalize = int(self.pending_finalize)
+        a.potential = C.pointer(self.pot)
+        if self.shells is not None:
+            a.shells = C.pointer(self.shells)
+        a.g_neighbour_dev = self.nl.data_ptr()
+        a.size, a.stride = self.size, self.stride
+        if self.kind == "andersen":
+            need = int(self.lib.hx_andersen_scratch_bytes(self.own_cap))
+            if getattr(self, "andersen_scratch", None) is None or self.andersen_scratch.numel() < need:
+                self.andersen_scratch = self.torch.empty(need, dtype=self.torch.uint8, device=self.vel.device)
+            a.rng = C.pointer(self.rng)
+            a.rng_state_dev = self.rng_state.data_ptr()
+            a.andersen_scratch_dev, a.andersen_scratch_bytes = self.andersen_scratch.data_ptr(), need
+            a.sqrt_temperature, a.coll_prob = self.sqrt_temperature, self.coll_prob
+        return a
+
     def run(self, steps):
-        """sampler:run(steps): chunks of speculatively enqueued steps with the device-resident rebuild test."""
-        hx, torch = self.hx, self.torch
+        """sampler:run(steps): chunks of speculatively enqueued steps (hx_dd_enqueue_steps: one C call per chunk, the
+        halo pushes, the rebuild vote and the guarded force of every step are device-side); the host looks at the
+        control block once per chunk."""
+        hx = self.hx
         steps = int(steps)
         if steps <= 0:
             return
@@ -542,19 +736,18 @@ class DecomposedSystem:
             predicted = max(self.last_interval - self.since_update, 1)
             chunk = int(min(max(self.min_chunk, min(self.max_chunk, predicted + 2)), remaining))
             self.ctl[1:3].zero_()          # halted flag and step counter; the running displacement maximum stays
-            for k in range(chunk):
-                self._verlet(fuse and (self.pending_finalize or k > 0), True, True)
-                if self.nranks > 1:
-                    self._halo_exchange(guard=True)
-                    self.ex.allreduce(self.ctl[0:1], "max")     # rebuild vote: every rank sees the global maximum
-                self._force(guarded=True)
-                if not fuse:
-                    self._andersen(True)
+            desc = self._steps_descriptor()
+            hx.check(self.lib.hx_dd_enqueue_steps(C.byref(desc), chunk, self.st), "hx_dd_enqueue_steps")
             ctl = self.ctl.cpu().numpy()
             self.stats["chunks"] += 1
             self.stats["syncs"] += 1
+            if int(ctl[3]) == 0xDEAD:
+                raise hx.HxError(f"rank {self.rank}: a peer did not reach step {self.step + int(ctl[2]) + 1} (halo wait timed out)")
             done, halted = int(ctl[2]), bool(ctl[1])
+            # every executed integration kernel switched the position buffer (the halted step's ran as well)
+            self.cur ^= (done + (1 if halted else 0)) & 1
             self.since_update += done
+            self.step += done
             if halted:
                 self.last_interval = max(self.since_update + 1, 1)
                 self.update_lists()
@@ -562,13 +755,13 @@ class DecomposedSystem:
                 if not fuse:
                     self._andersen(False)
                 done += 1
+                self.step += 1
                 self.since_update = 0
             elif self.since_update > self.last_interval:
                 self.last_interval = self.since_update
             if fuse:
                 self.pending_finalize = True
             remaining -= done
-            self.step += done
         self._finish_step()
         self.force_valid = True
 

@@ -436,6 +436,58 @@ int hx_gather_float4(const hx_float4* src_dev, const uint32_t* index_dev, size_t
                      const uint32_t* ctl_dev, void* stream);
 int hx_gather_u32(const uint32_t* src_dev, const uint32_t* index_dev, size_t n, uint32_t* dst_dev, void* stream);
 
+
+/* ---- decomposed step loop: halo exchange and rebuild vote over peer memory (NVLink), no host and no library collective
+ * between the kernels of a step.  Position buffers and inboxes are allocated with hx_dd_alloc (plain cudaMalloc, so that
+ * they can be exported), exported / mapped with the ipc functions (cudaIpc*), one process per GPU.
+ * hx_dd_enqueue_steps enqueues `chunk` MD steps, each:
+ *   fused Verlet kernel: position_dev[current] -> position_dev[current ^ 1] (owned particles, displacement maximum),
+ *   hx_gather_float4 of the send lists into peer_ghost_dev[dir][current ^ 1] (the neighbours' ghost slots, peer memory),
+ *   signal: {step, local maximum} into inbox slot [rank] of every other rank; wait: until all inbox slots of this
+ *   rank carry the step, global maximum folded into ctl[0] (spins at most timeout_cycles, then halts with ctl[3] =
+ *   0xDEAD), guarded pair force (private shell rows if `shells`, else the public rows) on position_dev[current ^ 1],
+ *   [Andersen half-kick if rng != NULL]; current ^= 1.
+ * A halted control block turns every later kernel of the chunk into a no-op on every rank at the same step (all
+ * ranks see the same global maximum).  step numbers are global: step_base = number of the last completed step. */
+#define HX_DD_MAX_RANKS 32
+#define HX_DD_IPC_HANDLE_BYTES 64
+typedef struct hx_dd_steps {
+    hx_float4* position_dev[2];
+    int current;
+    hx_float4 *image_dev, *velocity_dev, *force_dev;
+    const hx_float4* r0_dev;
+    size_t n_own, n_ghost, array_size;
+    float timestep;
+    float box_length[3];
+    int nranks, rank;
+    const uint32_t* send_index_dev[2];          /* owned particles pushed to the left / right neighbour */
+    size_t send_count[2];
+    hx_float4* peer_ghost_dev[2][2];            /* [direction][buffer]: this rank's block in the neighbour's buffers */
+    unsigned long long* const* peer_inbox_dev;  /* device array [nranks] of mapped inbox pointers */
+    const unsigned long long* inbox_dev;        /* own inbox: 2 rows (step parity) of HX_DD_MAX_RANKS words, zeroed at allocation */
+    long long timeout_cycles;
+    uint32_t* ctl_dev;
+    float skin_half;
+    uint64_t step_base;
+    int pending_finalize;                       /* velocities still lack the second half-kick of the last step */
+    const hx_lj_params* potential;
+    const hx_shell_rows* shells;                /* NULL: walk g_neighbour_dev */
+    const uint32_t* g_neighbour_dev;
+    unsigned size;
+    size_t stride;
+    const hx_rand48* rng;                       /* NULL: NVE */
+    uint16_t* rng_state_dev;
+    void* andersen_scratch_dev;
+    size_t andersen_scratch_bytes;
+    float sqrt_temperature, coll_prob;
+} hx_dd_steps;
+int hx_dd_alloc(size_t bytes, void** out_dev);
+int hx_dd_free(void* dev);
+int hx_dd_ipc_export(void* dev, unsigned char handle_out[HX_DD_IPC_HANDLE_BYTES]);
+int hx_dd_ipc_open(const unsigned char handle[HX_DD_IPC_HANDLE_BYTES], void** out_dev);
+int hx_dd_ipc_close(void* dev);
+int hx_dd_enqueue_steps(const hx_dd_steps* steps, unsigned chunk, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -143,11 +143,33 @@ def gpu_parity(rank, world, out):
             res[f"{tag}_nl_count"] = np.array([len(allsets[i]) for i in range(n)])
             res[f"{tag}_nl_flat"] = np.concatenate([allsets[i] for i in range(n)])
             res[f"{tag}_thermo"] = np.array([th["internal_energy"], th["potential_energy"], th["temperature"], th["pressure"]])
+            res[f"{tag}_vcm"] = np.array(th["center_of_mass_velocity"])
+
+    def ghost_check():
+        """Ghost slots must hold, bit for bit, the owners' current positions (the halo pushes of the last step)."""
+        s._finish_step()
+        torch.cuda.synchronize()
+        ntot = s.n_own + s.n_ghost
+        ids = s.id[:ntot].cpu().numpy().astype(np.int64)
+        pos = s.pos[:ntot].cpu().numpy()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (ids[:s.n_own], pos[:s.n_own]))
+        owner_pos = np.zeros((n, 4), dtype=np.float32)
+        for i, p in gathered:
+            owner_pos[i] = p
+        bad = int((pos[s.n_own:].view(np.uint32) != owner_pos[ids[s.n_own:]].view(np.uint32)).any(axis=1).sum())
+        t = torch.tensor([bad], dtype=torch.int64)
+        dist.all_reduce(t)
+        return int(t.item())
 
     snapshot("t0")
-    s.run(steps)
+    s.run(steps // 2)
+    stale = ghost_check()
+    s.run(steps - steps // 2)
+    stale += ghost_check()
     snapshot("t1")
     if rank == 0:
+        res["stale_ghosts"] = np.array([stale])
         res["updates"] = np.array([s.updates])
         res["migrated"] = np.array([s.stats["migrated"]])
         np.savez(out, **res)

@@ -104,9 +104,6 @@ def single_gpu_reference(n, steps):
     from halmd_b200 import simulation
     s = simulation.lennard_jones_fluid(n, seed=21)            # same generator calls as dd_worker.gpu_parity
     p = s.particle
-    # the decomposed loop walks the public rows: the same summation order is what makes the runs comparable bit by bit
-    from halmd_b200 import _lib as hx
-    hx.check(hx.lib.hxm_neighbour_set_shell_rows(s.neighbour._h, 0))
 
     def snap():
         s.force.apply()
@@ -162,6 +159,7 @@ def test_decomposed_run_matches_single_gpu(tmp_path, world, n, backend):
     # several ranks differ only by the summation order of the forces
     sets, rel = compare(b, r, "t1", n, bitwise=(world == 1), bitwise_force=(world == 1))
     assert int(r["updates"][0]) >= 2
+    assert int(r["stale_ghosts"][0]) == 0                  # halo pushes over peer memory: ghosts are the owners' current positions
     if world > 1:
         assert int(r["migrated"][0]) > 0
         L = (n / 0.8442) ** (1 / 3)
@@ -171,6 +169,10 @@ def test_decomposed_run_matches_single_gpu(tmp_path, world, n, backend):
         same = sum(np.array_equal(x, y) for x, y in zip(b["sets"], sets))
         assert same > 0.98 * n                             # sets may differ for pairs at the rounding edge of r_c + skin
         assert rel < 1e-2
+        # Newton's third law across the slab faces: both ranks must have used the same positions for every cross-boundary
+        # pair in every step, or the total momentum would drift (a ghost one step stale shifts v_cm by ~1e-6 per step)
+        assert np.abs(r["t1_vcm"] - r["t0_vcm"]).max() < 2e-7, r["t1_vcm"] - r["t0_vcm"]
+        assert abs(r["t1_thermo"][0] - r["t0_thermo"][0]) < 2e-5 * abs(r["t0_thermo"][0])      # total energy conserved
     else:
         assert all(np.array_equal(x, y) for x, y in zip(b["sets"], sets))
     assert np.allclose(b["thermo"][:2], r["t1_thermo"][:2], rtol=1e-5, atol=1e-5)

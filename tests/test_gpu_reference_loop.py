@@ -146,14 +146,16 @@ def test_thermodynamic_sums_against_reference_kernels(hx, cuda, refloop):
     d_out = dev.zeros(hx.THERMO_DOUBLES, np.float64)
     hx.check(hx.lib.hx_thermodynamics(dev.p(d_v), dev.p(d_e), dev.p(d_s), A, n, dev.p(d_out), dev.stream))
     out = dev.down(d_out)
-    # same per-particle terms; the reference accumulates them in double-single (~2^-44 per addition), the product in
-    # double
+    # Same per-particle terms.  The reference accumulates in double-single and its result carries up to float-epsilon
+    # relative error in some components (measured: 7e-8 in sum m v_y, 4e-10 in sum m v_x); the product sums in double.
     for k in range(7):
-        assert abs(out[k] - ref[k]) <= 2e-9 * max(abs(ref[k]), np.sqrt(n)), (k, out[k], ref[k])
-    # exact values (double) for both
-    v32 = vel[:n, :3]
-    ip = (v32[:, 2] * v32[:, 2] + (v32[:, 0] * v32[:, 0] + v32[:, 1] * v32[:, 1]))      # float inner product (order immaterial at 1e-7)
-    exact = np.array([(vel[:n, 3].astype(np.float64) * ip.astype(np.float64)).sum(),
-                      *(vel[:n, 3:4].astype(np.float64) * vel[:n, :3]).sum(axis=0), vel[:n, 3].astype(np.float64).sum(),
+        assert abs(out[k] - ref[k]) <= 2e-7 * max(abs(ref[k]), np.sqrt(n)), (k, out[k], ref[k])
+    # the product against the exact sums of the same terms (float inner product for the kinetic energy: its rounding
+    # is the only inexact step, hence the looser bound on component 0)
+    v64, m64 = vel[:n, :3].astype(np.float64), vel[:n, 3].astype(np.float64)
+    exact = np.array([(m64 * (v64 ** 2).sum(axis=1)).sum(), *(m64[:, None] * v64).sum(axis=0), m64.sum(),
                       en[:n].astype(np.float64).sum(), st.reshape(6, A)[:3, :n].astype(np.float64).sum()])
-    assert np.all(np.abs(out[:7] - exact) <= 3e-7 * np.maximum(np.abs(exact), np.sqrt(n)))
+    scale = np.array([(m64 * (v64 ** 2).sum(axis=1)).sum(), *np.abs(m64[:, None] * v64).sum(axis=0), m64.sum(),
+                      np.abs(en[:n]).astype(np.float64).sum(), np.abs(st.reshape(6, A)[:3, :n]).astype(np.float64).sum()])
+    tol = np.array([1e-7, 1e-13, 1e-13, 1e-13, 1e-13, 1e-13, 1e-13])
+    assert np.all(np.abs(out[:7] - exact) <= tol * scale), (out[:7] - exact) / scale
