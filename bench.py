@@ -340,8 +340,20 @@ def force_kernel_roofline(s, args, torch, bursts=12, per_burst=3):
         force = torch.empty(d.cap * 4, dtype=torch.float32, device="cuda")
 
         def launch():
-            hx.check(lib.hx_pair_force2(C.byref(d.pot), d._p(d.pos), d._p(d.pos), d.n_own + d.n_ghost, d._p(d.nl), d.size, d.stride,
-                                        hx.LAYOUT_ROW, n, d.Lf, 1, 0.5, force.data_ptr(), None, None, d.cap, None, 0.0, st))
+            if d.shells is not None:
+                hx.check(lib.hx_pair_force_shells(C.byref(d.pot), d._p(d.pos), d._p(d.pos), C.byref(d.shells), d._p(d.r0), n, d.Lf,
+                                                  hx.FORCE_POSITIONS_REDUCED, 1, force.data_ptr(), d._p(d.ctl), d.skin_half, st))
+            else:
+                hx.check(lib.hx_pair_force2(C.byref(d.pot), d._p(d.pos), d._p(d.pos), d.n_own + d.n_ghost, d._p(d.nl), d.size, d.stride,
+                                            hx.LAYOUT_ROW, n, d.Lf, 1, 0.5, force.data_ptr(), None, None, d.cap, None, 0.0, st))
+        if d.shells is not None and d.nranks == 1:
+            kernel = "k_force_shell (private shell-ordered rows, prefix walk, packed f32x2, 4 lanes per particle)"
+
+            def advance():
+                d.run(4)
+                d._finish_step()
+                if not d.lists_valid:
+                    d.update_lists()
     else:
         p, nb, pot = s.particle, s.neighbour, s.potential
         n = p.nparticle
@@ -520,7 +532,7 @@ def run_ours(args, cfg):
 
     # end to end through the public API with host buffers: H2D of the state, block of MD steps, D2H of the results
     if decomposed:
-        st0 = s.dd.local_state()
+        st0 = s.dd.download()
         pos_h, vel_h = st0["position"], st0["velocity"]
     else:
         pos_h = s.particle.get("position_ds")
@@ -534,7 +546,7 @@ def run_ours(args, cfg):
         if decomposed:
             s.dd.upload(pos_h, vel_h)
             s.run(md)
-            st1 = s.dd.local_state()
+            st1 = s.dd.download()
             # (ownership may have changed during the block: the next upload uses the new arrays)
             pos_h, vel_h = st1["position"], st1["velocity"]
         else:
@@ -555,12 +567,34 @@ def run_ours(args, cfg):
         h2d, d2h = int(t[0].item()), int(t[1].item())
         halo_bytes = torch.tensor([float(s.dd.ex.bytes_sent)], device="cuda", dtype=torch.float64) if decomposed else None
 
+    dd_stats = dict(s.dd.stats, bytes_sent_rank0=int(s.dd.ex.bytes_sent)) if decomposed else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     core_stats = s.core.stats() if single else None
+    one_rank = None
+    if decomposed and world > 1 and not args.no_extra:
+        # the same decomposed code on one rank with the same number of particles per GPU: the denominator of the
+        # weak-scaling efficiency (rank 0 only; the other ranks have left)
+        del s
+        torch.cuda.empty_cache()
+        from halmd_b200 import simulation
+        dd1 = simulation.decomposed_lj_fluid(n_rank, 0, 1, seed=1, integrator="andersen", timestep=0.005, rate=2.0)
+        dd1.run(min(args.melt_steps, 300))
+        dd1.set_integrator("verlet", timestep=0.001)
+        dd1.run(md)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        dd1.run(2 * md)
+        f1.record(stream)
+        torch.cuda.synchronize()
+        t1 = f0.elapsed_time(f1) * 1e-3
+        one_rank = {"value": n_rank * 2 * md / t1, "unit": "particle-steps/s", "particles": n_rank, "md_steps": 2 * md, "stats": dict(dd1.stats), "updates": dd1.updates,
+                    "what": "the decomposed step loop on ONE rank (no neighbours) with the same particles per GPU"}
+        s = DecomposedAdapter(dd1)
     roof = force_kernel_roofline(s, args, torch)
     cpu = gpu_ref = None
     extra = {}
@@ -587,8 +621,10 @@ def run_ours(args, cfg):
             torch.cuda.empty_cache()
     e_drift = abs(th1["internal_energy"] - th0["internal_energy"]) / abs(th0["internal_energy"])
     if decomposed:
-        par = f"slab domain decomposition along x over {world} GPU(s), {n_rank} particles per GPU, ghost exchange + rebuild vote every step (NCCL)"
-        core = dict(s.dd.stats, bytes_sent_rank0=int(s.dd.ex.bytes_sent))
+        par = (f"slab domain decomposition along x over {world} GPU(s), {n_rank} particles per GPU; every step the boundary particles' "
+               "positions are stored into the neighbours' ghost slots over peer memory (NVLink) and the rebuild vote travels "
+               "through per-rank inboxes, device-side wait, no host or library collective inside a step; NCCL only at list updates")
+        core = dd_stats
     else:
         par = "single GPU" if world == 1 else f"{world} independent replicas (one per GPU)"
         core = core_stats
@@ -609,7 +645,8 @@ def run_ours(args, cfg):
         "gpu_reference": gpu_ref,
         "detail": {"ns_per_particle_step": 1e9 * elapsed / (world * n_rank * md * args.steps), "list_updates": int(nupdates),
                    "md_steps": md * args.steps, "steps_per_update": md * args.steps / max(nupdates, 1),
-                   "energy_drift_rel": e_drift, "temperature": th1["temperature"], "core": core, **extra},
+                   "energy_drift_rel": e_drift, "temperature": th1["temperature"], "core": core, "per_gpu_1rank": one_rank,
+                   "per_gpu": value / world, **extra},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -298,11 +298,10 @@ __global__ void __launch_bounds__(SB_WARPS * 32) k_shell_rows(shell_build_args a
 #pragma unroll
     for (unsigned c = lane; c < HX_NSHELL * SB_SLOTS; c += 32) s_cnt[w][c] = 0;
     __syncwarp();
-    for (unsigned slot = 0; slot < nslot; ++slot) {
+    // classification of one entry: gather, distance as in the list build, thresholds, rank within (slot, shell)
+    auto classify = [&](unsigned slot, unsigned j, float4 const& r2) {
         unsigned const k = slot * 32 + lane;
         bool const valid = k < cnt;
-        unsigned const j = valid ? src[k] : i;
-        float4 const r2 = a.pos2[j];
         float const dx = minimg(__fsub_rn(r1.x, r2.x), a.L.x, a.invL.x);
         float const dy = minimg(__fsub_rn(r1.y, r2.y), a.L.y, a.invL.y);
         float const dz = minimg(__fsub_rn(r1.z, r2.z), a.L.z, a.invL.z);
@@ -319,6 +318,24 @@ __global__ void __launch_bounds__(SB_WARPS * 32) k_shell_rows(shell_build_args a
             s_j[w][k] = j;
             s_sr[w][k] = static_cast<unsigned char>(sh | (rank << 3));
         }
+    };
+    // the kernel is latency-bound (index load -> position gather -> arithmetic): the first four slots (128 entries,
+    // nearly every list) have their index loads, then their gathers, in flight together
+    {
+        unsigned jj[4];
+        float4 rj[4];
+#pragma unroll
+        for (unsigned q = 0; q < 4; ++q) jj[q] = (q * 32 + lane < cnt) ? src[q * 32 + lane] : i;
+#pragma unroll
+        for (unsigned q = 0; q < 4; ++q) rj[q] = a.pos2[jj[q]];
+#pragma unroll
+        for (unsigned q = 0; q < 4; ++q)
+            if (q < nslot) classify(q, jj[q], rj[q]);
+    }
+    for (unsigned slot = 4; slot < nslot; ++slot) {
+        unsigned const k = slot * 32 + lane;
+        unsigned const j = k < cnt ? src[k] : i;
+        classify(slot, j, a.pos2[j]);
     }
     __syncwarp();
     // exclusive scan over the HX_NSHELL * SB_SLOTS = 128 cells in (shell, slot) order: 4 consecutive cells per lane

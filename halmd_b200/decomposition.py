@@ -141,6 +141,45 @@ class Exchange:
         for t, w in post:
             t.copy_(w)
 
+    def sendrecv_many(self, items):
+        """Several (leftward, rightward, from_right, from_left) exchanges issued as ONE batch of point-to-point operations."""
+        if self.nranks == 1:
+            return
+        dist, ops, post = self.dist, [], []
+        for k, (leftward, rightward, from_right, from_left) in enumerate(items):
+            for t, peer, tag, is_send in ((leftward, self.left, 2 * k, True), (from_right, self.right, 2 * k, False),
+                                          (rightward, self.right, 2 * k + 1, True), (from_left, self.left, 2 * k + 1, False)):
+                if t is None or t.numel() == 0:
+                    continue
+                if is_send:
+                    w = self._wire(t.contiguous())
+                    self.bytes_sent += w.numel() * w.element_size()
+                    ops.append(dist.P2POp(dist.isend, w, peer, self.group, tag))
+                else:
+                    if self.stage and t.is_cuda:
+                        w = self.torch.empty(t.shape, dtype=t.dtype, device="cpu")
+                        post.append((t, w))
+                    else:
+                        assert t.is_contiguous()
+                        w = t
+                    ops.append(dist.P2POp(dist.irecv, w, peer, self.group, tag))
+        if ops:
+            for work in dist.batch_isend_irecv(ops):
+                work.wait()
+        for t, w in post:
+            t.copy_(w)
+
+    def allgather_ints(self, values):
+        """values (a few Python ints) of every rank: list of lists, one collective and one host read."""
+        if self.nranks == 1:
+            return [list(values)]
+        torch = self.torch
+        dev = "cpu" if self.stage else "cuda"
+        mine = torch.tensor(list(values), dtype=torch.int64, device=dev)
+        out = torch.empty(self.nranks * len(values), dtype=torch.int64, device=dev)
+        self.dist.all_gather_into_tensor(out, mine, group=self.group)
+        return out.cpu().numpy().reshape(self.nranks, len(values)).tolist()
+
     def exchange_counts(self, n_leftward, n_rightward):
         """Sizes of the messages about to arrive: (from_right, from_left)."""
         if self.nranks == 1:
@@ -296,7 +335,7 @@ class DecomposedSystem:
         self.sort_scratch = torch.empty(self.sort_bytes, dtype=torch.uint8, device=dev)
         self.counts = z(4, dtype=i32)
         self.ctl = z(4, dtype=i32)
-        self.flags = z(2, dtype=i32)
+        self.flags = z(4, dtype=i32)
         self.g_cell = torch.empty(self.ncells * self.cell_size, dtype=i32, device=dev)
         self.cell_count = z(self.ncells, dtype=i32)
         self.nl = torch.empty(self.own_cap * self.stride, dtype=i32, device=dev)
@@ -335,6 +374,7 @@ class DecomposedSystem:
             hx.check(self.lib.hx_rand48_seed(C.byref(self.rng), 32, 256, int(seed) + 7919 * rank, self._p(self.rng_state), self.st))
             self.set_temperature(temperature, rate)
         self.use_shells = True
+        self._staging = {}
         self.shells, self.shell_rows, self.shell_ends = None, None, None
         self.timeout_cycles = int(20e9)            # ~10 s of SM clock: a rank that never arrives stops the chunk
         self.lists_valid = False
@@ -467,18 +507,29 @@ class DecomposedSystem:
             raise hx.HxError(f"rank {self.rank}: owned particles {n_new} exceed the capacity {self.own_cap}")
         a, b = n_stay, n_stay + n_l           # send blocks [a, b) leftward and [b, n) rightward
         c, d = n_stay, n_stay + from_right    # arrivals: [c, d) from the right, [d, n_new) from the left
-        # arrivals overwrite the send blocks, so the outgoing records are staged first
-        def blocks(lo, hi):
-            return [self.pos[lo:hi].clone(), self.pos[cap + lo:cap + hi].clone(), self.vel[lo:hi].clone(),
-                    self.vel[cap + lo:cap + hi].clone(), self.image[lo:hi].clone(), self.id[lo:hi].clone()]
+        # one message per direction: the full record of a particle (position and velocity words, image, id) as 21 floats;
+        # arrivals overwrite the send blocks, so the outgoing records are packed first
+        pos, vel = self.pos, self.vel
 
-        def slots(lo, hi):
-            return [self.pos[lo:hi], self.pos[cap + lo:cap + hi], self.vel[lo:hi], self.vel[cap + lo:cap + hi],
-                    self.image[lo:hi], self.id[lo:hi]]
-        out_l, out_r = blocks(a, b), blocks(b, n)
-        in_r, in_l = slots(c, d), slots(d, n_new)
-        for k in range(6):
-            self.ex.sendrecv(out_l[k], out_r[k], in_r[k], in_l[k])
+        def pack(lo, hi):
+            if hi == lo:
+                return None
+            return torch.cat([pos[lo:hi], pos[cap + lo:cap + hi], vel[lo:hi], vel[cap + lo:cap + hi], self.image[lo:hi],
+                              self.id[lo:hi].view(torch.float32).unsqueeze(1)], dim=1)
+
+        def unpack(rec, lo, hi):
+            if hi == lo:
+                return
+            pos[lo:hi], pos[cap + lo:cap + hi] = rec[:, 0:4], rec[:, 4:8]
+            vel[lo:hi], vel[cap + lo:cap + hi] = rec[:, 8:12], rec[:, 12:16]
+            self.image[lo:hi] = rec[:, 16:20]
+            self.id[lo:hi] = rec[:, 20].contiguous().view(torch.int32)
+        out_l, out_r = pack(a, b), pack(b, n)
+        in_r = torch.empty(from_right, 21, dtype=torch.float32, device=pos.device) if from_right else None
+        in_l = torch.empty(from_left, 21, dtype=torch.float32, device=pos.device) if from_left else None
+        self.ex.sendrecv(out_l, out_r, in_r, in_l)
+        unpack(in_r, c, d)
+        unpack(in_l, d, n_new)
         self.stats["migrated"] += n_l + n_r
         self.n_own = n_new
 
@@ -512,20 +563,36 @@ class DecomposedSystem:
             counts[dest] = m
         if self.nranks == 1:
             return
-        from_right, from_left = self.ex.exchange_counts(counts["left"], counts["right"])
+        # one collective tells every rank what it needs: the sizes of the blocks about to arrive and where its own blocks
+        # land in the neighbours' buffers (slot offset, which of their two position buffers is current)
+        meta = self.ex.allgather_ints([n, counts["left"], counts["right"], self.cur])
+        L, R = dec.left, dec.right
+        if self.nranks == 2:
+            from_right, from_left = meta[R][1], 0          # the peer's single combined list arrives as its leftward message
+        else:
+            from_right, from_left = meta[R][1], meta[L][2]
         total = n + from_right + from_left
         if total > self.cap:
             raise hx.HxError(f"rank {self.rank}: owned + ghost particles {total} exceed the capacity {self.cap}")
         self.n_ghost_from = {"right": from_right, "left": from_left}
         self.n_ghost = from_right + from_left
-        self._halo_exchange(guard=False)
-        # ghost ids (diagnostics, neighbour-set parity tests)
+        # my leftward block is the left neighbour's `from_right` block (behind its owned particles); my rightward block
+        # lands behind the right neighbour's owned particles and its own `from_right` block
+        self.peer_offset = {"left": meta[L][0], "right": meta[R][0] + (meta[(R + 1) % self.nranks][1] if self.nranks > 2 else 0)}
+        # relative orientation of my two position buffers and each neighbour's, fixed until the next list update (every
+        # executed step switches the current buffer on all ranks alike)
+        self.peer_flip = {"left": meta[L][3] ^ self.cur, "right": meta[R][3] ^ self.cur}
+        # ghost positions and ids (diagnostics, neighbour-set parity tests) in one batch of messages
         ids = {}
         for dest in ("left", "right"):
-            ids[dest] = torch.empty(counts[dest], dtype=torch.int32, device=self.pos.device)
-            if counts[dest]:
-                hx.check(self.lib.hx_gather_u32(self._p(self.id), self._p(self.send_idx[dest]), counts[dest], self._p(ids[dest]), self.st))
-        self.ex.sendrecv(ids["left"], ids["right"], self.id[n:n + from_right], self.id[n + from_right:total])
+            m = counts[dest]
+            ids[dest] = torch.empty(m, dtype=torch.int32, device=self.pos.device)
+            if m:
+                hx.check(self.lib.hx_gather_float4(self._p(self.pos), self._p(self.send_idx[dest]), m, self._p(self.send_buf[dest]), None, self.st))
+                hx.check(self.lib.hx_gather_u32(self._p(self.id), self._p(self.send_idx[dest]), m, self._p(ids[dest]), self.st))
+        fr, fl = from_right, from_left
+        self.ex.sendrecv_many([(self.send_buf["left"], self.send_buf["right"], self.pos[n:n + fr], self.pos[n + fr:n + fr + fl]),
+                               (ids["left"], ids["right"], self.id[n:n + fr], self.id[n + fr:total])])
 
     def _halo_exchange(self, guard=True):
         """Current positions (high words, species tag) of the fixed ghost sets: pack, exchange, land in the ghost slots."""
@@ -550,12 +617,12 @@ class DecomposedSystem:
             hx.check(self.lib.hx_nlist_build2(self._p(self.g_cell), self.ncell, self.cell_size, self._p(self.pos), ntot, self.n_own,
                                               self.rr_cut_skin, self.nt, self.nt, self.Lf, self._p(self.nl), self.size, self.stride,
                                               hx.LAYOUT_ROW, 0, self._p(self.nl_count), self._p(self.flags, 1), self.st), "nlist")
-            fl = self.flags.cpu().numpy()
+            hx.check(self.lib.hx_count_max(self._p(self.nl_count), self.n_own, self._p(self.flags, 2), self.st), "count_max")
+            # every rank must take the same decision: the cell grid and list size are global properties (and the longest
+            # list, which sizes the private shell rows, may as well be); one reduction, one host read
+            self.ex.allreduce(self.flags, "max")
+            f0, f1, self.longest_list = (int(v) for v in self.flags.cpu().numpy()[:3])
             self.stats["syncs"] += 1
-            # every rank must take the same decision: the cell grid and list size are global properties
-            both = torch.tensor([int(fl[0]), int(fl[1])], dtype=torch.int32, device=self.pos.device)
-            self.ex.allreduce(both, "max")
-            f0, f1 = (int(v) for v in both.cpu().numpy())
             if f0:
                 # binning.cpp:216-219 — overcrowded cells: double the cell size
                 self.cell_size *= 2
@@ -576,14 +643,25 @@ class DecomposedSystem:
     def update_lists(self):
         """neighbour update: on_prepend_update (migration + sort) -> binning -> lists -> displacement zero."""
         hx = self.hx
+        import time
+        self.torch.cuda.synchronize()
+        t0 = time.perf_counter()
         self._migrate()
+        t1 = time.perf_counter()
         self._order()
         self._ghosts()
+        self.torch.cuda.synchronize()
+        t2 = time.perf_counter()
         self._build()
         hx.check(self.lib.hx_displacement_zero(self._p(self.pos), self._p(self.r0), self.n_own, self.st))
         hx.check(self.lib.hx_ctl_reset(self._p(self.ctl), self.st))
         self._build_shells()
-        self._exchange_landing()
+        self.torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        self.stats["update_ms"] = self.stats.get("update_ms", 0.0) + 1e3 * (t3 - t0)
+        self.stats["migrate_ms"] = self.stats.get("migrate_ms", 0.0) + 1e3 * (t1 - t0)
+        self.stats["order_ghosts_ms"] = self.stats.get("order_ghosts_ms", 0.0) + 1e3 * (t2 - t1)
+        self.stats["build_ms"] = self.stats.get("build_ms", 0.0) + 1e3 * (t3 - t2)
         self.lists_valid = True
         self.updates += 1
 
@@ -593,10 +671,7 @@ class DecomposedSystem:
         self.shells = None
         if not self.use_shells or self.n_own == 0:
             return
-        hx.check(self.lib.hx_count_max(self._p(self.nl_count), self.n_own, self._p(self.counts), self.st), "count_max")
-        longest = int(self.counts[0].item())
-        self.stats["syncs"] += 1
-        pitch = (longest + 32) // 32 * 32
+        pitch = (self.longest_list + 32) // 32 * 32
         if pitch > 512:
             return
         words = int(self.lib.hx_shell_rows_words(self.own_cap, pitch))
@@ -610,25 +685,6 @@ class DecomposedSystem:
         hx.check(self.lib.hx_shell_rows_build(C.byref(self.pot), self._p(self.nl), self.stride, self._p(self.nl_count), self._p(self.pos),
                                               self._p(self.pos), self.n_own, self.Lf, C.byref(sh), self.st), "shell_rows")
         self.shells = sh
-
-    def _exchange_landing(self):
-        """Tell the two neighbours where their ghost blocks land in this rank's position buffers (slot offset and
-        which of the two buffers is current): the step loop stores straight into those slots (peer memory)."""
-        if self.nranks == 1:
-            return
-        torch = self.torch
-        fr = self.n_ghost_from["right"]
-        dev = "cpu" if self.ex.stage else self.vel.device
-        to_left = torch.tensor([self.n_own + fr, self.cur], dtype=torch.int64, device=dev)    # for the sender of `from_left`
-        to_right = torch.tensor([self.n_own, self.cur], dtype=torch.int64, device=dev)        # for the sender of `from_right`
-        of_right, of_left = torch.zeros_like(to_left), torch.zeros_like(to_left)
-        self.ex.sendrecv(to_left, to_right, of_right, of_left)
-        # my leftward block is the left neighbour's `from_right` block: it told me (rightward message) where it lands
-        of_left, of_right = of_left.cpu().numpy(), of_right.cpu().numpy()
-        self.peer_offset = {"left": int(of_left[0]), "right": int(of_right[0])}
-        # relative orientation of my two buffers and each neighbour's, fixed until the next list update (every executed
-        # step switches the current buffer on all ranks alike)
-        self.peer_flip = {"left": int(of_left[1]) ^ self.cur, "right": int(of_right[1]) ^ self.cur}
 
     # ---- forces, integration ------------------------------------------------------------------------------------------
     def _force(self, aux=False, guarded=False):
@@ -794,30 +850,63 @@ class DecomposedSystem:
         self.ex.allreduce(c, "sum")
         return float(t.item() / c.item())
 
-    def local_state(self):
-        """Host copies of this rank's owned particles: ids, positions (double), velocities (double), forces."""
+    def _pinned(self, name, shape, dtype):
+        buf = self._staging.get(name)
+        if buf is None or buf.shape[0] < shape[0]:
+            buf = self.torch.empty((int(shape[0] * 1.1) + 1024,) + tuple(shape[1:]), dtype=dtype, pin_memory=True)
+            self._staging[name] = buf
+        return buf[:shape[0]]
+
+    def download(self):
+        """particle:get of positions and velocities of the owned particles as double-precision host arrays: the
+        double-single planes are joined on the device and leave through pinned staging buffers (48 bytes per particle)."""
+        torch = self.torch
         self._finish_step()
-        self._ensure_force()
         n, cap = self.n_own, self.cap
-        ph, pl = self.pos[:n, :3].double().cpu().numpy(), self.pos[cap:cap + n, :3].double().cpu().numpy()
-        vh, vl = self.vel[:n, :3].double().cpu().numpy(), self.vel[cap:cap + n, :3].double().cpu().numpy()
-        return {"id": self.id[:n].cpu().numpy().astype(np.int64), "position": ph + pl, "velocity": vh + vl,
-                "force": self.force[:n, :3].cpu().numpy(), "image": self.image[:n, :3].cpu().numpy()}
+        out = {}
+        for name, arr in (("position", self.pos), ("velocity", self.vel)):
+            joined = arr[:n, :3].double() + arr[cap:cap + n, :3].double()
+            host = self._pinned(name, (n, 3), torch.float64)
+            host.copy_(joined, non_blocking=True)
+            out[name] = host
+        torch.cuda.current_stream().synchronize()
+        return {k: v.numpy() for k, v in out.items()}
+
+    def local_state(self):
+        """Host copies of this rank's owned particles: ids, positions (double), velocities (double), forces, images."""
+        self._ensure_force()
+        n = self.n_own
+        st = {k: v.copy() for k, v in self.download().items()}
+        st.update({"id": self.id[:n].cpu().numpy().astype(np.int64), "force": self.force[:n, :3].cpu().numpy(),
+                   "image": self.image[:n, :3].cpu().numpy()})
+        return st
 
     def upload(self, positions, velocities):
-        """Replace positions and velocities of the owned particles (same order as local_state()) from host arrays
-        (double, split into double-single words); as particle:set(), this invalidates lists and forces."""
-        torch, n, cap = self.torch, self.n_own, self.cap
+        """particle:set of positions and velocities of the owned particles (same order as download()) from double host
+        arrays, split into double-single words on the device (dsdeq, dsfun.hpp:122-126).  As in the single-GPU module
+        layer, the neighbour lists stay valid unless some particle now lies further than skin / 2 from where it was at
+        the last list update (the displacement test is re-evaluated over all ranks); ghosts are refreshed."""
+        torch, hx, n, cap = self.torch, self.hx, self.n_own, self.cap
         self._finish_step()
-        dev = self.pos.device
-        for arr, host in ((self.pos, positions), (self.vel, velocities)):
-            host = np.asarray(host, dtype=np.float64)
-            hi = host.astype(np.float32)
-            lo = (host - hi.astype(np.float64)).astype(np.float32)
-            arr[:n, :3] = torch.from_numpy(hi).to(dev, non_blocking=True)
-            arr[cap:cap + n, :3] = torch.from_numpy(lo).to(dev, non_blocking=True)
-        self.lists_valid = False
+        for name, arr, host in (("position", self.pos, positions), ("velocity", self.vel, velocities)):
+            src = torch.from_numpy(np.ascontiguousarray(host, dtype=np.float64))
+            stage = self._staging.get(name)
+            if stage is not None and src.data_ptr() == stage.data_ptr() and src.shape[0] == n:
+                stage = stage[:n]                  # the caller hands back the pinned buffer download() returned
+            else:
+                stage = self._pinned(name + "_up", (n, 3), torch.float64)
+                stage.copy_(src)
+            x = stage.to(arr.device, non_blocking=True)
+            hi = x.float()
+            arr[:n, :3] = hi
+            arr[cap:cap + n, :3] = (x - hi.double()).float()
         self.force_valid = False
+        if self.lists_valid:
+            self._halo_exchange(guard=False)
+            hx.check(self.lib.hx_displacement_max(self._p(self.pos), self._p(self.r0), n, self.Lf, self._p(self.ctl), 1, self.st))
+            self.ex.allreduce(self.ctl[0:1], "max")
+            if self.lib.hx_displacement_exceeds(int(self.ctl[0].item()) & 0xFFFFFFFF, self.skin) != 0:
+                self.lists_valid = False
 
     def neighbour_sets(self):
         """{global id: sorted global ids of its neighbours} for the owned particles (parity tests)."""

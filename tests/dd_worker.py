@@ -158,9 +158,9 @@ def gpu_parity(rank, world, out):
         for i, p in gathered:
             owner_pos[i] = p
         bad = int((pos[s.n_own:].view(np.uint32) != owner_pos[ids[s.n_own:]].view(np.uint32)).any(axis=1).sum())
-        t = torch.tensor([bad], dtype=torch.int64)
-        dist.all_reduce(t)
-        return int(t.item())
+        counts = [None] * world
+        dist.all_gather_object(counts, bad)
+        return int(sum(counts))
 
     snapshot("t0")
     s.run(steps // 2)
