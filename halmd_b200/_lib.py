@@ -165,6 +165,7 @@ _protos = {
     "hx_density_modes": (C.c_int, [P, SZ, P, C.c_uint, P, P]),
     "hx_thermodynamics": (C.c_int, [P, P, P, SZ, SZ, P, P]),
     "hx_wavevector_pick": (C.c_int, [D3, C.c_uint, D3, C.c_double, C.c_uint, U3, D3, C.c_uint, U3]),
+    "hx_isf_accumulate": (C.c_int, [D3, D3, U3, C.c_uint, C.c_double, D3]),
     "hx_ctl_reset": (C.c_int, [P, P]),
     "hx_nlist_build2": (C.c_int, [P, U3, C.c_uint, P, SZ, SZ, F3, C.c_uint, C.c_uint, F3, P, C.c_uint, SZ,
                                   C.c_int, C.c_int, P, P, P]),
@@ -255,6 +256,7 @@ _module_protos = {
     "hxm_blocking_isf": (C.c_int, [P, D3]),
     "hxm_blocking_mqd": (C.c_int, [P, D3]),
     "hxm_blocking_vacf": (C.c_int, [P, D3]),
+    "hxm_blocking_trace": (C.c_int, [P, C.c_int, C.POINTER(U64), C.c_size_t, C.POINTER(C.c_size_t)]),
     "hxm_core_run_sampling": (C.c_int, [P, U64, P]),
 }
 MODULE_SYMBOLS = tuple(_module_protos)

@@ -649,6 +649,15 @@ class _blocking_scheme(_Handle):
     def finalise(self):
         check(lib.hxm_blocking_finalise(self._h))
 
+    def trace(self, enable=True):
+        """Parity diagnostics: start (or stop and clear) recording, and return the (level, first step, later step) triples
+        of all sample pairs correlated so far, in the order correlation<>::compute visits them."""
+        n = C.c_size_t(0)
+        check(lib.hxm_blocking_trace(self._h, 1, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 3), dtype=np.uint64)
+        check(lib.hxm_blocking_trace(self._h, 1 if enable else 0, out.ctypes.data_as(C.POINTER(C.c_uint64)), n.value, None))
+        return out
+
     def _result(self, fn, extra):
         shape = (self.levels, self.size) + extra + (3,)
         out = np.zeros(shape)

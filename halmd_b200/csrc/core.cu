@@ -334,4 +334,33 @@ int hx_wavevector_pick(const double* wavenumber, unsigned nwavenumber, const dou
     return HX_OK;
 }
 
+// intermediate_scattering_function.hpp:90-113 with the accumulator of numeric/accumulator.hpp:56-132 (value update
+// :64-70, merge :104-118) in the reference's operation order
+int hx_isf_accumulate(const double* rho1, const double* rho2, const unsigned* shell_offsets, unsigned nshell, double norm,
+                      double* acc)
+{
+    if (!rho1 || !rho2 || !shell_offsets || !acc) { set_error("hx_isf_accumulate: invalid argument"); return HX_E_INVALID; }
+    for (unsigned s = 0; s < nshell; ++s) {
+        double n = 0, m = 0, v = 0;
+        for (unsigned i = shell_offsets[s]; i < shell_offsets[s + 1]; ++i) {
+            double const re = rho1[2 * i] * rho2[2 * i] + rho1[2 * i + 1] * rho2[2 * i + 1];
+            double const x = re / norm;
+            double const t = x - m;
+            n += 1;
+            m += t / n;
+            v += t * (x - m);
+        }
+        if (n > 0) {
+            double* const a = acc + 3 * static_cast<size_t>(s);
+            double const count = a[0] + n;
+            a[2] += v;
+            double const diff = a[1] - m;
+            a[2] += diff * diff * a[0] * n / count;
+            a[1] = (a[0] * a[1] + n * m) / count;
+            a[0] = count;
+        }
+    }
+    return HX_OK;
+}
+
 } // extern "C"

@@ -661,6 +661,8 @@ struct hxm_blocking {
     size_t msd_scratch_bytes = 0;
     const float4** d_ptrs = nullptr;
     double norm = 1;
+    bool trace_on = false;                   // record (level, first step, second step) of every correlated sample pair
+    std::vector<uint64_t> trace;
 
     ~hxm_blocking()
     {
@@ -736,19 +738,15 @@ struct hxm_blocking {
             }
             if (nq > 0) {
                 // intermediate_scattering_function.hpp:90-113
-                auto const& rho1 = block[0]->rho;
-                for (unsigned k = 0; k < nl; ++k) {
-                    auto const& rho2 = block[k]->rho;
-                    for (unsigned s = 0; s < nshell; ++s) {
-                        welford acc;
-                        for (unsigned i = shell_offsets[s]; i < shell_offsets[s + 1]; ++i) {
-                            double re = rho1[2 * i] * rho2[2 * i] + rho1[2 * i + 1] * rho2[2 * i + 1];
-                            welford_add(acc, re / norm);
-                        }
-                        welford_merge(isf[(level * block_size + k) * nshell + s], acc);
-                    }
-                }
+                static_assert(sizeof(welford) == 3 * sizeof(double), "welford is (count, mean, M2)");
+                for (unsigned k = 0; k < nl; ++k)
+                    HXM_TRY(hx_isf_accumulate(block[0]->rho.data(), block[k]->rho.data(), shell_offsets.data(), nshell, norm,
+                                              &isf[(level * block_size + k) * nshell].n));
             }
+            if (trace_on)
+                for (unsigned k = 0; k < nl; ++k) {
+                    trace.push_back(level); trace.push_back(block[0]->step); trace.push_back(block[k]->step);
+                }
         }
         uint64_t skip = std::max<uint64_t>((separation + interval[level] - 1) / interval[level], 1);
         origin[level] += skip * interval[level];
@@ -1480,6 +1478,20 @@ int hxm_blocking_isf(hxm_blocking* b, double* out)
 {
     if (!b || !out) return HX_E_INVALID;
     for (size_t i = 0; i < b->isf.size(); ++i) { out[3 * i] = b->isf[i].n; out[3 * i + 1] = b->isf[i].m; out[3 * i + 2] = b->isf[i].v; }
+    return 0;
+}
+
+int hxm_blocking_trace(hxm_blocking* b, int enable, uint64_t* events_out, size_t capacity, size_t* nevents_out)
+{
+    if (!b) return HX_E_INVALID;
+    b->trace_on = enable != 0;
+    size_t const n = b->trace.size() / 3;
+    if (nevents_out) *nevents_out = n;
+    if (events_out) {
+        if (capacity < n) { set_error("hxm_blocking_trace: capacity %zu < %zu events", capacity, n); return HX_E_INVALID; }
+        std::copy(b->trace.begin(), b->trace.end(), events_out);
+    }
+    if (!enable) b->trace.clear();
     return 0;
 }
 

@@ -363,6 +363,13 @@ int hx_wavevector_pick(const double* wavenumber, unsigned nwavenumber, const dou
                        unsigned max_count, const unsigned* filter, double* vectors_out, unsigned capacity,
                        unsigned* shell_offsets_out);
 
+/* intermediate_scattering_function::operator() (halmd/observables/dynamics/intermediate_scattering_function.hpp:90-113), host
+ * side, no device work: for every wavevector shell s (wavevectors shell_offsets[s] .. shell_offsets[s + 1]) the values
+ * Re[rho1 conj(rho2)] / norm are accumulated (numeric/accumulator.hpp:56-132) and the shell's accumulator is merged into
+ * acc[3 * s + {0,1,2}] = (count, mean, M2), in place.  rho: (re, im) per wavevector. */
+int hx_isf_accumulate(const double* rho1, const double* rho2, const unsigned* shell_offsets, unsigned nshell, double norm,
+                      double* acc);
+
 /* thermodynamic sums over particles i < n, as doubles:
  * out[0]=sum m v^2, out[1..3]=sum m v, out[4]=sum m, out[5]=sum en_pot, out[6]=sum virial trace
  * (halmd/observables/gpu/thermodynamics_kernel.cu:35-97).  en_pot/stress may be NULL.

@@ -184,6 +184,10 @@ int hxm_blocking_isf(hxm_blocking* b, double* out);
  * out[(level * block_size + lag) * 3 + {0,1,2}] = (count, mean, M2) like hxm_blocking_msd */
 int hxm_blocking_mqd(hxm_blocking* b, double* out);
 int hxm_blocking_vacf(hxm_blocking* b, double* out);
+/* diagnostics for parity tests: with enable != 0 every correlated sample pair is recorded as (level, step of the first
+ * sample of the block, step of the later sample) in the order correlation<>::compute visits them
+ * (correlation.hpp:208-224); events_out (3 * capacity words) may be NULL to query *nevents_out only.  enable == 0 stops and clears. */
+int hxm_blocking_trace(hxm_blocking* b, int enable, uint64_t* events_out, size_t capacity, size_t* nevents_out);
 /* run `steps` steps sampling the blocking scheme at every step that a level is due (sampler on_sample slot) */
 int hxm_core_run_sampling(hxm_core* c, uint64_t steps, hxm_blocking* b);
 

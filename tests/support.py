@@ -255,3 +255,63 @@ def pack_state(pos, species=None, vel=None, mass=None):
 
 def species_of(p, A):
     return p[:A, 3].view(np.uint32)
+
+
+def blocking_reference(n_steps, dt, max_lag, resolution, size, shift, separation, start=0, finalise=True):
+    """Pure-Python restatement of blocking_scheme.cpp:75-200 (schedule only): returns the list of
+    (level, [sample steps of the block]) correlation events.  Pinned against the reference's own classes compiled in
+    place (tests/test_oracle_ref.py::test_blocking_schedule_against_reference_classes)."""
+    max_interval = int(round(max_lag / dt))
+    s = int(round(resolution / dt))
+    interval = []
+    while s <= max_interval:
+        interval.append(s)
+        if shift > 1 and s * shift <= max_interval:
+            interval.append(s * shift)
+        s *= size
+    origin = [start] * len(interval)
+    blocks = [[] for _ in interval]
+    events = []
+
+    def process(i):
+        events.append((i, list(blocks[i])))
+        skip = max((separation + interval[i] - 1) // interval[i], 1)
+        origin[i] += skip * interval[i]
+        del blocks[i][:skip]
+
+    for step in range(start, start + n_steps + 1):
+        for i, iv in enumerate(interval):
+            if step >= origin[i] and (step - origin[i]) % iv == 0:
+                blocks[i].append(step)
+                if len(blocks[i]) == size:
+                    process(i)
+    for i in range(len(interval) if finalise else 0):
+        while blocks[i]:
+            process(i)
+    return interval, events
+
+
+def ref_blocking_schedule(ref, dt, max_lag, resolution, size, shift, separation, start, n_steps, finalise=True):
+    """The reference's own clock + blocking_scheme + samples::blocking_scheme + correlation<> classes (oracle/ref_dynamics.cpp)
+    driven like sampler:run; returns (intervals, events[(level, first, second)], count[level, lag], mean lag in steps, time grid)."""
+    max_levels, max_events = 64, 4 * (n_steps + 2) * size + 1024
+    iv = np.zeros(max_levels, dtype=np.uint64)
+    ev = np.zeros((max_events, 3), dtype=np.uint64)
+    nev = C.c_uint64(0)
+    cnt, mean, time = (np.zeros(max_levels * size) for _ in range(3))
+    fn = ref.ref_blocking_schedule
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_double, C.c_double, C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p,
+                   C.c_uint, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p]
+    levels = fn(dt, max_lag, resolution, size, shift, separation, start, n_steps, 1 if finalise else 0, iv.ctypes.data, max_levels,
+                ev.ctypes.data, max_events, C.byref(nev), cnt.ctypes.data, mean.ctypes.data, time.ctypes.data)
+    if levels < 0:
+        return None
+    n = levels * size
+    return ([int(x) for x in iv[:levels]], ev[:nev.value].astype(np.int64), cnt[:n].reshape(levels, size),
+            mean[:n].reshape(levels, size), time[:n].reshape(levels, size))
+
+
+def blocking_events(events):
+    """(level, [steps]) blocks of blocking_reference as (level, first, second) triples in correlation order."""
+    return np.array([(lev, blk[0], st) for lev, blk in events for st in blk], dtype=np.int64).reshape(-1, 3)

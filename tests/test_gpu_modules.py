@@ -282,37 +282,36 @@ def test_kob_andersen_mixture(api):
     assert sp.sum() == 32000 - int(0.8 * 32000)
 
 
-def blocking_reference(n_steps, dt, max_lag, resolution, size, shift, separation):
-    """Pure-Python restatement of blocking_scheme.cpp:75-200 (schedule only): returns the list of
-    (level, [sample steps of the block]) correlation events."""
-    max_interval = int(round(max_lag / dt))
-    s = int(round(resolution / dt))
-    interval = []
-    while s <= max_interval:
-        interval.append(s)
-        if shift > 1 and s * shift <= max_interval:
-            interval.append(s * shift)
-        s *= size
-    origin = [0] * len(interval)
-    blocks = [[] for _ in interval]
-    events = []
+blocking_reference = support.blocking_reference
 
-    def process(i):
-        events.append((i, list(blocks[i])))
-        skip = max((separation + interval[i] - 1) // interval[i], 1)
-        origin[i] += skip * interval[i]
-        del blocks[i][:skip]
 
-    for step in range(n_steps + 1):
-        for i, iv in enumerate(interval):
-            if step >= origin[i] and (step - origin[i]) % iv == 0:
-                blocks[i].append(step)
-                if len(blocks[i]) == size:
-                    process(i)
-    for i in range(len(interval)):
-        while blocks[i]:
-            process(i)
-    return interval, events
+@pytest.mark.parametrize("case", [(0.12, 4, 5, 2, 3, 37, 240), (0.9, 10, 10, 3, 10, 0, 1210), (0.4, 3, 3, 2, 50, 11, 700)])
+def test_blocking_scheme_pairs_against_reference_classes(api, ref, case):
+    """sampler:run with a blocking scheme (hxm_core_run_sampling + hxm_blocking): the sequence of correlated sample pairs
+    (level, step of the first sample of the block, step of the later sample) equals that of the reference's own clock,
+    blocking_scheme, sample-buffer and correlation classes compiled in place (oracle/ref_dynamics.cpp:
+    blocking_scheme.cpp:34-200, samples/blocking_scheme.hpp, correlation.hpp:208-224) driven like sampler.cpp:63-80."""
+    halmd_b200, simulation = api
+    from halmd_b200 import observables
+    max_lag, every, size, shift, sep, start, steps = case
+    s = simulation.lennard_jones_fluid(500, seed=3)
+    core = halmd_b200.mdsim.core.get()
+    s.run(start)
+    dt = s.integrator.timestep
+    step0 = core.step
+    bs = observables.dynamics.blocking_scheme(max_lag=max_lag, every=every, size=size, shift=shift, separation=sep)
+    bs.trace()
+    observables.sampler.run(steps, blocking_scheme=bs)
+    before = bs.trace()
+    bs.finalise()
+    after = bs.trace(enable=False)
+    for fin, mine in ((False, before), (True, after)):
+        iv, ev, cnt, _, time = support.ref_blocking_schedule(ref, dt, max_lag, every * dt, size, shift, sep, step0, steps, finalise=fin)
+        assert bs.interval == iv
+        assert np.array_equal(mine.astype(np.int64), ev), (case, fin)
+        assert np.array_equal(bs.time, time)
+    msd = bs.mean_square_displacement()
+    assert np.array_equal(msd["count"], cnt * 500)
 
 
 def test_blocking_scheme_msd_and_isf(api):
