@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS),
                     help="default: cfg2 on one GPU, cfg4 (domain-decomposed, weak scaling) on several")
     ap.add_argument("--n-per-gpu", type=int, default=None, help="particles per GPU of the decomposed workload (cfg4)")
+    ap.add_argument("--n-total", type=int, default=None,
+                    help="total particles of the decomposed workload, divided evenly over the GPUs: strong scaling (cfg4)")
     ap.add_argument("--md-steps", type=int, default=None, help="MD steps per bench step (default 1000; 200 for cfg4)")
     ap.add_argument("--layout", default="row", choices=["row", "column"])
     ap.add_argument("--lanes", type=int, default=4)
@@ -68,6 +70,9 @@ def parse():
     if a.config is None:
         a.config = "cfg2" if a.gpus == 1 else "cfg4"
     dd = CONFIGS[a.config]["kind"] == "lj-dd"
+    a.strong = bool(dd and a.n_total)
+    if a.strong:
+        a.n_per_gpu = a.n_total // max(a.gpus, 1)
     if a.md_steps is None:
         a.md_steps = 200 if dd else 1000
     if a.melt_steps is None:
@@ -630,7 +635,8 @@ def run_ours(args, cfg):
         core = core_stats
     line = {
         "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
+        "scaling": "strong" if getattr(args, "strong", False) else "weak",
         "vs_baseline": None, "dtype": "f32 pair math, double-single (2xf32) state, compensated f32 force sums", "data": "synthetic",
         "config": {"workload": cfg["workload"], "md_steps_per_bench_step": md, "neighbour_layout": args.layout, "lanes_per_particle": args.lanes,
                    "particles_total": world * n_rank, "parallelism": par,
@@ -656,6 +662,9 @@ def run_ours(args, cfg):
 def main():
     args = parse()
     cfg = CONFIGS[args.config]
+    if args.strong:
+        cfg = dict(cfg, workload=cfg["workload"].replace(
+            "N=8,000,000 per GPU (64M on 8 GPUs)", f"N={args.n_per_gpu * args.gpus:,} in total, {args.n_per_gpu:,} per GPU (strong scaling)"))
     if args.impl == "reference":
         run_reference(args, cfg)
     else:

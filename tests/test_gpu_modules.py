@@ -294,7 +294,7 @@ def test_blocking_scheme_pairs_against_reference_classes(api, ref, case):
     halmd_b200, simulation = api
     from halmd_b200 import observables
     max_lag, every, size, shift, sep, start, steps = case
-    s = simulation.lennard_jones_fluid(500, seed=3)
+    s = simulation.lennard_jones_fluid(1500, seed=3)
     core = halmd_b200.mdsim.core.get()
     s.run(start)
     dt = s.integrator.timestep
@@ -311,7 +311,7 @@ def test_blocking_scheme_pairs_against_reference_classes(api, ref, case):
         assert np.array_equal(mine.astype(np.int64), ev), (case, fin)
         assert np.array_equal(bs.time, time)
     msd = bs.mean_square_displacement()
-    assert np.array_equal(msd["count"], cnt * 500)
+    assert np.array_equal(msd["count"], cnt * 1500)
 
 
 def test_blocking_scheme_msd_and_isf(api):
