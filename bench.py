@@ -372,7 +372,9 @@ def force_kernel_roofline(s, args, torch, bursts=12, per_burst=3):
         kind = s.kind
 
         def launch():
-            # as the module layer launches it inside the step loop (positions reduced by the integrator)
+            # as the module layer launches it inside the step loop (positions reduced by the integrator); the position
+            # buffers swap at list updates and inside chunks: the pointer is fetched per launch
+            pos = p.device_ptr("position")
             sh = lib.hxm_neighbour_named_ptr(nb._h, b"shell_rows")
             if sh:
                 hx.check(lib.hx_pair_force_shells(C.byref(par), pos, pos, C.cast(sh, C.POINTER(hx.ShellRows)),

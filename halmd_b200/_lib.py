@@ -46,6 +46,12 @@ class ShellRows(C.Structure):
     _fields_ = [("rows_dev", C.c_void_p), ("ends_dev", C.c_void_p), ("pitch", C.c_uint), ("delta", C.c_float * NSHELL)]
 
 
+class VerletTail(C.Structure):
+    _fields_ = [("position_out_dev", C.c_void_p), ("velocity_dev", C.c_void_p), ("image_dev", C.c_void_p),
+                ("array_size", C.c_size_t), ("timestep", C.c_float), ("max_rr_word_in", C.c_uint)]
+
+
+CTL_WORDS = 8
 DD_MAX_RANKS, DD_IPC_HANDLE_BYTES = 32, 64
 
 
@@ -140,6 +146,8 @@ _protos = {
     "hx_shell_rows_build": (C.c_int, [C.POINTER(LjParams), P, SZ, P, P, P, SZ, F3, C.POINTER(ShellRows), P]),
     "hx_pair_force_shells": (C.c_int, [C.POINTER(LjParams), P, P, C.POINTER(ShellRows), P, SZ, F3, C.c_int, C.c_int, P, P,
                                        C.c_float, P]),
+    "hx_pair_force_shells_verlet": (C.c_int, [C.POINTER(LjParams), P, C.POINTER(ShellRows), P, SZ, F3, C.c_int, P, P, C.c_float,
+                                              C.POINTER(VerletTail), P]),
     "hx_verlet_integrate": (C.c_int, [P, P, P, P, SZ, C.c_float, F3, P]),
     "hx_verlet_finalize": (C.c_int, [P, P, SZ, C.c_float, P]),
     "hx_verlet_finalize_integrate": (C.c_int, [P, P, P, P, SZ, SZ, C.c_float, F3, C.c_int, P, P, P]),
@@ -243,6 +251,7 @@ _module_protos = {
     "hxm_core_run": (C.c_int, [P, U64]),
     "hxm_core_step": (U64, [P]),
     "hxm_core_set_chunk": (C.c_int, [P, C.c_uint, C.c_uint]),
+    "hxm_core_set_fused_verlet": (C.c_int, [P, C.c_int]),
     "hxm_core_stats": (C.c_int, [P, C.POINTER(U64), C.POINTER(U64), C.POINTER(U64)]),
     "hxm_core_thermodynamics": (C.c_int, [P, D3]),
     "hxm_blocking_create": (C.c_int, [P, C.c_double, C.c_double, C.c_uint, C.c_uint, C.c_uint, F3, C.c_uint, U3, C.c_uint, PP]),

@@ -469,6 +469,9 @@ class _core(_Handle):
     def set_chunk(self, lo, hi):
         check(lib.hxm_core_set_chunk(self._h, int(lo), int(hi)))
 
+    def set_fused_verlet(self, enable):
+        check(lib.hxm_core_set_fused_verlet(self._h, 1 if enable else 0))
+
     def stats(self):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         check(lib.hxm_core_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))

@@ -27,41 +27,7 @@ __global__ void k_state_init(float4* pos, float4* vel, float4* image, float4* fo
 }
 
 // ---- velocity-Verlet ---------------------------------------------------------------------------------
-struct ds3 { ds x, y, z; };
-
-// a += p * q with the product fused into the double-single sum and into its error term: what nvcc makes of
-// `v += f * (timestep / 2) / mass` in the reference build (verlet_kernel.cu:59, SASS of oracle/_ref/obj/verlet_kernel.o:
-// FFMA rcp(m), f * h, v.hi ... FFMA rcp(m), f * h, -e), i.e. dsadd (dsfun.hpp:142-152) with b = (p * q exactly, 0)
-__device__ __forceinline__ ds ds_add_prod(ds a, float p, float q)
-{
-    float t1 = __fmaf_rn(p, q, a.hi);
-    float e = __fsub_rn(t1, a.hi);
-    float t2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmaf_rn(p, q, -e), __fsub_rn(a.hi, __fsub_rn(t1, e))), a.lo), 0.f);
-    ds c;
-    c.hi = __fadd_rn(t1, t2);
-    c.lo = __fsub_rn(t2, __fsub_rn(c.hi, t1));
-    return c;
-}
-
-// v += f * (dt/2) / m: float product, division as the reference build divides (-prec-div=false: multiplication by
-// MUFU.RCP(m); exact for unit and power-of-two masses), fused into the double-single add
-__device__ __forceinline__ void half_kick(ds3& v, float4 f, float half_dt, float mass)
-{
-    float const rm = rcp_approx(mass);
-    v.x = ds_add_prod(v.x, rm, __fmul_rn(f.x, half_dt));
-    v.y = ds_add_prod(v.y, rm, __fmul_rn(f.y, half_dt));
-    v.z = ds_add_prod(v.z, rm, __fmul_rn(f.z, half_dt));
-}
-
-// r += v * dt;  image = rint(r_hi / L);  r -= image * L      (verlet_kernel.cu:60-62, box_kernel.cuh:37-45); the
-// quotient is r_hi * MUFU.RCP(L) as in the reference build (it decides the image only within an ulp of a half-integer)
-__device__ __forceinline__ float drift_wrap(ds& r, ds v, float dt, float L)
-{
-    r = ds_add(r, ds_mul(v, make_ds(dt)));
-    float image = rintf(__fmul_rn(rcp_approx(L), r.hi));
-    r = ds_sub(r, make_ds(__fmul_rn(image, L)));
-    return image;
-}
+// (ds3, ds_add_prod, half_kick, drift_wrap: common.cuh — shared with the fused tail of the shell force kernel)
 
 // 16-byte load that the compiler keeps in program order (ahead of the halted test below)
 __device__ __forceinline__ float4 ld_ordered(const float4* p)

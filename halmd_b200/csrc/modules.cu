@@ -72,6 +72,7 @@ struct hxm_particle {
     cudaStream_t st = nullptr;
     float4 *pos = nullptr, *vel = nullptr, *image = nullptr, *force = nullptr;
     float4 *pos_b = nullptr, *vel_b = nullptr, *image_b = nullptr;     // back buffers for rearrange
+    float4* pos_c = nullptr;       // second position buffer of the fused force + Verlet chain (hxm_core::run)
     float *en_pot = nullptr, *stress = nullptr;
     uint32_t *id = nullptr, *rid = nullptr, *id_b = nullptr;
     // cache counters (halmd/utility/cache.hpp): bumped on every write access
@@ -101,7 +102,7 @@ struct hxm_particle {
 
     ~hxm_particle()
     {
-        dev_free(pos); dev_free(vel); dev_free(image); dev_free(force); dev_free(pos_b); dev_free(vel_b);
+        dev_free(pos); dev_free(vel); dev_free(image); dev_free(force); dev_free(pos_b); dev_free(vel_b); dev_free(pos_c);
         dev_free(image_b); dev_free(en_pot); dev_free(stress); dev_free(id); dev_free(rid); dev_free(id_b);
         dev_free(io_dev);
         if (scratch) cudaFree(scratch);
@@ -187,7 +188,7 @@ struct hxm_neighbour {
     bool shells_valid = false;
     // max_displacement
     float4* r0 = nullptr;
-    uint32_t* ctl = nullptr;       // device control block (4 words), ctl[0] = max rr bits
+    uint32_t* ctl = nullptr;       // device control block (HX_CTL_WORDS words), ctl[0] = max rr bits, ctl[4] = second slot
     uint32_t* h_ctl = nullptr;     // pinned mirror
     // sorts.hilbert
     unsigned depth = 0;
@@ -498,6 +499,11 @@ struct hxm_core {
     hxm_integrator* integrator = nullptr;
     uint64_t step = 0;
     unsigned min_chunk = 2, max_chunk = 64;
+    // NVE: velocity-Verlet update in the tail of the shell force kernel.  Off by default: measured on B200 at config 2 the
+    // chain is 3.6 % slower than separate launches (75.8 vs 73.0 us per step) — the force kernel is issue-bound, so the
+    // integrator's instructions (one coordinate per lane, 8 particles per warp) add to its critical path, while the
+    // stand-alone k_verlet is latency-bound and overlaps the tail of the force kernel under programmatic dependent launch
+    bool fused_verlet = false;
     unsigned last_interval = 16;      // steps between the last two list updates (chunk length predictor)
     uint64_t steps_since_update = 0;
     uint64_t stat_launches = 0, stat_chunks = 0, stat_syncs = 0;
@@ -545,21 +551,59 @@ struct hxm_core {
         while (remaining > 0) {
             unsigned predicted = last_interval > steps_since_update ? static_cast<unsigned>(last_interval - steps_since_update) : 1;
             unsigned chunk = std::min<uint64_t>(std::max(min_chunk, std::min(max_chunk, predicted + 2)), remaining);
-            // reset halted flag and step counter, keep the running maximum displacement
-            HXM_CUDA(cudaMemsetAsync(nb->ctl + CTL_HALTED, 0, 2 * sizeof(uint32_t), p->st));
+            // reset halted flag, step counter (and the second displacement slot), keep the running maximum displacement
+            HXM_CUDA(cudaMemsetAsync(nb->ctl + CTL_HALTED, 0, (CTL_MAX_RR_B - CTL_HALTED + 1) * sizeof(uint32_t), p->st));
             p->reduced = true;      // the integration kernel reduces every position before the force kernel reads it
-            for (unsigned k = 0; k < chunk; ++k) {
+            // NVE with private shell rows and no further force contributions: all steps of the chunk but the first
+            // integrate in the tail of the force kernel of the step before (one launch per step)
+            bool const chain = fuse && fused_verlet && chunk > 1 && f->walls.empty() && nb->shells_valid
+                               && nb->shell_potential == &f->potential->p;
+            if (chain) {
                 HXM_TRY(hx_verlet_finalize_integrate(
                     reinterpret_cast<hx_float4*>(p->pos), reinterpret_cast<hx_float4*>(p->image),
                     reinterpret_cast<hx_float4*>(p->vel), reinterpret_cast<hx_float4*>(p->force), p->n, p->A, dt, in->Lf,
-                    (fuse && (pending_finalize || k > 0)) ? 1 : 0, reinterpret_cast<hx_float4*>(nb->r0), nb->ctl, p->st));
-                HXM_TRY(f->compute(false, nb->ctl, skin_half));
-                if (!fuse) HXM_TRY(in->finalize_kernel(nb->ctl));
+                    pending_finalize ? 1 : 0, reinterpret_cast<hx_float4*>(nb->r0), nb->ctl, p->st));
+                float4* const buf[2] = {p->pos, p->pos_c};
+                unsigned const word[2] = {CTL_MAX_RR, CTL_MAX_RR_B};
+                hx_verlet_tail t;
+                t.velocity_dev = reinterpret_cast<hx_float4*>(p->vel);
+                t.image_dev = reinterpret_cast<hx_float4*>(p->image);
+                t.array_size = p->A;
+                t.timestep = dt;
+                int cur = 0;
+                for (unsigned k = 0; k < chunk; ++k) {
+                    bool const last = k + 1 == chunk;
+                    t.position_out_dev = last ? nullptr : reinterpret_cast<hx_float4*>(buf[cur ^ 1]);
+                    t.max_rr_word_in = word[cur];
+                    HXM_TRY(hx_pair_force_shells_verlet(&f->potential->p, reinterpret_cast<hx_float4*>(buf[cur]), &nb->shells,
+                                                        reinterpret_cast<hx_float4*>(nb->r0), p->n, f->Lf, HX_FORCE_POSITIONS_REDUCED,
+                                                        last ? reinterpret_cast<hx_float4*>(p->force) : nullptr, nb->ctl, skin_half,
+                                                        &t, p->st));
+                    if (!last) cur ^= 1;
+                }
+            } else {
+                for (unsigned k = 0; k < chunk; ++k) {
+                    HXM_TRY(hx_verlet_finalize_integrate(
+                        reinterpret_cast<hx_float4*>(p->pos), reinterpret_cast<hx_float4*>(p->image),
+                        reinterpret_cast<hx_float4*>(p->vel), reinterpret_cast<hx_float4*>(p->force), p->n, p->A, dt, in->Lf,
+                        (fuse && (pending_finalize || k > 0)) ? 1 : 0, reinterpret_cast<hx_float4*>(nb->r0), nb->ctl, p->st));
+                    HXM_TRY(f->compute(false, nb->ctl, skin_half));
+                    if (!fuse) HXM_TRY(in->finalize_kernel(nb->ctl));
+                }
             }
-            HXM_CUDA(cudaMemcpyAsync(nb->h_ctl, nb->ctl, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, p->st));
+            HXM_CUDA(cudaMemcpyAsync(nb->h_ctl, nb->ctl, HX_CTL_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, p->st));
             HXM_CUDA(cudaStreamSynchronize(p->st));
             stat_chunks++;
             stat_syncs++;
+            if (chain) {
+                // fused launches completed before the chunk ended or halted: an odd number leaves the current positions in
+                // the second buffer and the running maximum displacement in the second slot
+                uint64_t const fused_done = std::min<uint64_t>(nb->h_ctl[CTL_STEPS], chunk - 1);
+                if (fused_done & 1u) {
+                    std::swap(p->pos, p->pos_c);
+                    HXM_CUDA(cudaMemcpyAsync(nb->ctl + CTL_MAX_RR, nb->ctl + CTL_MAX_RR_B, sizeof(uint32_t), cudaMemcpyDeviceToDevice, p->st));
+                }
+            }
             uint64_t done = nb->h_ctl[CTL_STEPS];
             bool halted = nb->h_ctl[CTL_HALTED] != 0;
             p->pos_ver += done + (halted ? 1 : 0);
@@ -797,6 +841,7 @@ int hxm_particle_create(size_t nparticle, unsigned nspecies, void* stream, hxm_p
     size_t A = p->A;
     HXM_TRY(dev_alloc(&p->pos, 2 * A)); HXM_TRY(dev_alloc(&p->vel, 2 * A)); HXM_TRY(dev_alloc(&p->image, A));
     HXM_TRY(dev_alloc(&p->force, A)); HXM_TRY(dev_alloc(&p->pos_b, 2 * A)); HXM_TRY(dev_alloc(&p->vel_b, 2 * A));
+    HXM_TRY(dev_alloc(&p->pos_c, 2 * A));
     HXM_TRY(dev_alloc(&p->image_b, A)); HXM_TRY(dev_alloc(&p->en_pot, A)); HXM_TRY(dev_alloc(&p->stress, 6 * A));
     HXM_TRY(dev_alloc(&p->id, A)); HXM_TRY(dev_alloc(&p->rid, A)); HXM_TRY(dev_alloc(&p->id_b, A));
     HXM_TRY(hx_state_init(reinterpret_cast<hx_float4*>(p->pos), reinterpret_cast<hx_float4*>(p->vel),
@@ -804,6 +849,8 @@ int hxm_particle_create(size_t nparticle, unsigned nspecies, void* stream, hxm_p
                           p->n, A, p->st));
     HXM_CUDA(cudaMemsetAsync(p->en_pot, 0, A * sizeof(float), p->st));
     HXM_CUDA(cudaMemsetAsync(p->stress, 0, 6 * A * sizeof(float), p->st));
+    // (the padding entries behind nparticle are never written again: both buffers of the fused chain hold the initial values)
+    HXM_CUDA(cudaMemcpyAsync(p->pos_c, p->pos, 2 * A * sizeof(float4), cudaMemcpyDeviceToDevice, p->st));
     HXM_CUDA(cudaStreamSynchronize(p->st));
     *out = p.release();
     return 0;
@@ -1098,15 +1145,15 @@ int hxm_neighbour_create(hxm_particle* particle, const double box_length[3], con
     HXM_TRY(dev_alloc(&nb->count, n));
     HXM_TRY(dev_alloc(&nb->flag, 1));
     HXM_TRY(dev_alloc(&nb->r0, n));
-    HXM_TRY(dev_alloc(&nb->ctl, 4));
+    HXM_TRY(dev_alloc(&nb->ctl, HX_CTL_WORDS));
     HXM_TRY(dev_alloc(&nb->keys, particle->A));
     HXM_TRY(dev_alloc(&nb->index, particle->A));
     nb->sort_scratch_bytes = hx_sort_scratch_bytes(n);
     HXM_CUDA(cudaMalloc(&nb->sort_scratch, nb->sort_scratch_bytes));
     HXM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&nb->h_flag), 4 * sizeof(int)));
     HXM_TRY(dev_alloc(&nb->count_max, 1));
-    HXM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&nb->h_ctl), 4 * sizeof(uint32_t)));
-    HXM_TRY(hx_ctl_reset(nb->ctl, particle->st));
+    HXM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&nb->h_ctl), HX_CTL_WORDS * sizeof(uint32_t)));
+    HXM_CUDA(cudaMemsetAsync(nb->ctl, 0, HX_CTL_WORDS * sizeof(uint32_t), particle->st));
     nb->depth = hx_hilbert_depth(box_length);
     if (occupancy <= 0) occupancy = 0.4;          // from_binning.cpp:284-287
     HXM_TRY(nb->set_occupancy(occupancy));
@@ -1346,6 +1393,13 @@ int hxm_core_set_chunk(hxm_core* c, unsigned min_chunk, unsigned max_chunk)
     if (!c || min_chunk == 0 || max_chunk < min_chunk) return HX_E_INVALID;
     c->min_chunk = min_chunk;
     c->max_chunk = max_chunk;
+    return 0;
+}
+
+int hxm_core_set_fused_verlet(hxm_core* c, int enable)
+{
+    if (!c) return HX_E_INVALID;
+    c->fused_verlet = enable != 0;
     return 0;
 }
 

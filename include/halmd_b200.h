@@ -231,6 +231,30 @@ int hx_pair_force_shells(const hx_lj_params* potential, const hx_float4* positio
                          size_t nparticle, const float box_length[3], int flags /* HX_FORCE_POSITIONS_REDUCED */, int force_zero,
                          hx_float4* force_dev, uint32_t* ctl_dev, float skin_half, void* stream);
 
+/* The same kernel with the velocity-Verlet update of the particle fused into its tail, for the device-resident step
+ * loop: after the force on particle i is summed, the second half-kick of this step (verlet_kernel.cu:73-98) and the first
+ * half-step of the next one (verlet_kernel.cu:37-68: half-kick, drift, periodic wrap + image) are applied to i with the
+ * arithmetic of hx_verlet_finalize_integrate, and its squared displacement from r0 (max_displacement_kernel.cu:36-68)
+ * is accumulated.  The new positions go to position_out_dev (hi plane, lo plane at + array_size), which must not be the
+ * buffer the kernel gathers from; velocities and images are updated in place; the force array is not written.
+ * The control block (HX_CTL_WORDS words) holds two slots of the running maximum squared displacement, words 0 and 4: the
+ * launch tests slot max_rr_word_in like hx_pair_force_guarded and accumulates into the other slot (carrying the running
+ * maximum over), so that blocks which start late never see displacements of this launch.  position_out_dev == NULL: plain
+ * guarded force kernel (forces to force_dev) that tests slot max_rr_word_in — the last launch of a chunk. */
+#define HX_CTL_WORDS 8
+typedef struct hx_verlet_tail {
+    hx_float4* position_out_dev;
+    hx_float4* velocity_dev;
+    hx_float4* image_dev;
+    size_t array_size;
+    float timestep;
+    unsigned max_rr_word_in;    /* 0 or 4 */
+} hx_verlet_tail;
+int hx_pair_force_shells_verlet(const hx_lj_params* potential, const hx_float4* position_dev, const hx_shell_rows* shells,
+                                const hx_float4* r0_dev, size_t nparticle, const float box_length[3], int flags,
+                                hx_float4* force_dev, uint32_t* ctl_dev, float skin_half, const hx_verlet_tail* tail,
+                                void* stream);
+
 /* ---- f1: external one-body force, planar Lennard-Jones 9-3 walls -----------------------------------------------
  * halmd/mdsim/gpu/forces/external.hpp:120-190, external_kernel.cuh:49-103,
  * halmd/mdsim/gpu/potentials/external/planar_wall.cpp:40-112, planar_wall_kernel.cu:43-105.

@@ -153,6 +153,10 @@ int hxm_core_run(hxm_core* c, uint64_t steps);
 uint64_t hxm_core_step(const hxm_core* c);
 /* chunk length bounds for hxm_core_run (default 2..64, adaptive) */
 int hxm_core_set_chunk(hxm_core* c, unsigned min_chunk, unsigned max_chunk);
+/* NVE with private shell rows: integrate in the tail of the pair-force kernel (hx_pair_force_shells_verlet): one launch
+ * per step instead of two.  Results are bit-identical either way; default off (measured 3.6 % slower at config 2 on B200:
+ * the pair-force kernel is issue-bound and the stand-alone integrator overlaps its tail). */
+int hxm_core_set_fused_verlet(hxm_core* c, int enable);
 /* statistics of the last run: kernels launched, chunks, host synchronisations */
 int hxm_core_stats(const hxm_core* c, uint64_t* launches, uint64_t* chunks, uint64_t* syncs);
 /* observables.thermodynamics: out[0]=E_kin/N, [1]=E_pot/N, [2]=virial/N, [3]=temperature, [4]=pressure,

@@ -22,6 +22,41 @@ def state_bytes(p):
     return [p.get(k).tobytes() for k in ("position_ds", "velocity_ds", "image", "id", "reverse_id")]
 
 
+def test_fused_verlet_tail_equals_separate_kernels(api):
+    """The velocity-Verlet update fused into the tail of the shell force kernel (hx_pair_force_shells_verlet: one launch per
+    step, double-buffered positions, two displacement slots) leaves exactly the state of the separate k_verlet +
+    k_force_shell launches — one species and the Kob-Andersen table, across list updates and halted chunks, for runs
+    split at arbitrary points."""
+    halmd_b200, simulation = api
+    from halmd_b200 import mdsim
+    a = simulation.lennard_jones_fluid(4000, seed=9)
+    b = simulation.lennard_jones_fluid(4000, seed=9)
+    a.core.set_fused_verlet(True)
+    b.core.set_fused_verlet(False)
+    for steps in (1, 2, 3, 250, 7, 137):
+        a.run(steps)
+        b.run(steps)
+        assert state_bytes(a.particle) == state_bytes(b.particle), steps
+    assert a.neighbour.updates == b.neighbour.updates and a.neighbour.updates >= 5
+    assert a.core.stats()["launches"] < 0.7 * b.core.stats()["launches"]
+    assert np.array_equal(a.particle.get("force"), b.particle.get("force"))
+    ta, tb = a.thermodynamics(), b.thermodynamics()
+    assert ta == tb
+    # mixture (species table in shared memory), NVE after a short thermostatted start
+    systems = []
+    for fused in (True, False):
+        s = simulation.kob_andersen_mixture(8000, seed=4)
+        s.run(100)
+        integ = mdsim.integrators.verlet(box=s.box, particle=s.particle, timestep=0.002)
+        s.integrator, s.core = integ, mdsim.core.get()
+        s.core.set_fused_verlet(fused)
+        s.core.set_chunk(2, 17)
+        s.run(300)
+        systems.append(s)
+    assert state_bytes(systems[0].particle) == state_bytes(systems[1].particle)
+    assert systems[0].neighbour.updates == systems[1].neighbour.updates
+
+
 def test_chunked_run_equals_single_steps(api):
     """sampler:run with the device-resident rebuild decision and fused kernels reproduces, bit for bit, the state of
     the reference call order (integrate, displacement check on the host, rebuild, force, finalize per step)."""
