@@ -265,6 +265,8 @@ struct hxm_neighbour {
             if (h_flag[0]) {
                 // binning.cpp:216-219 — overcrowded cells: double the cell size
                 HXM_TRY(binning->set_cell_size(2 * binning->cell_size));
+                // the list size follows the cell size (from_binning::set_occupancy, from_binning.cpp:96-119)
+                HXM_TRY(set_occupancy(nu_cell));
                 continue;
             }
             if (h_flag[1]) {

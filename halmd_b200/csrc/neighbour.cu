@@ -259,6 +259,68 @@ __global__ void __launch_bounds__(NL_THREADS) k_nlist_build(nlist_args a)
     }
 }
 
+// Cells too large for the shared-memory staging (27 * cell_size entries; strongly inhomogeneous systems, where the
+// reference keeps doubling the cell size: binning.cpp:216-219): the same lists straight from global memory.  One block
+// per home cell, one warp per home particle at a time, the 27 cells in the reference's visiting order, 32 slots per trip.
+template <bool ROW>
+__global__ void __launch_bounds__(NL_THREADS) k_nlist_build_direct(nlist_args a)
+{
+    unsigned const cell = blockIdx.x;
+    unsigned const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned const lane_lt = (1u << lane) - 1u;
+    unsigned const cs = a.cell_size;
+    const unsigned* const home = a.g_cell + static_cast<size_t>(cell) * cs;
+    if (home[0] >= a.nbuild) return;
+    int const cx = cell % a.ncell.x;
+    int const cy = (cell / a.ncell.x) % a.ncell.y;
+    int const cz = cell / a.ncell.x / a.ncell.y;
+    bool const typed = a.ntype1 * a.ntype2 > 1;
+    for (unsigned p = warp; p < cs; p += NL_WARPS) {
+        unsigned const n = home[p];
+        if (n >= a.nbuild) break;                  // placeholder, or a partner-only particle (ascending indices)
+        float4 const r1 = a.pos_hi[n];
+        unsigned* const row = ROW ? a.g_neighbour + static_cast<size_t>(n) * a.stride : a.g_neighbour + n;
+        unsigned count = 0;
+        for (unsigned k = 0; k < 27; ++k) {
+            int dx, dy, dz;
+            visit_offset(k, dx, dy, dz);
+            unsigned const c = (wrap_cell(cz, dz, a.ncell.z) * a.ncell.y + wrap_cell(cy, dy, a.ncell.y)) * a.ncell.x
+                               + wrap_cell(cx, dx, a.ncell.x);
+            const unsigned* const src = a.g_cell + static_cast<size_t>(c) * cs;
+            for (unsigned base = 0; base < cs; base += 32) {
+                unsigned const m = src[base + lane];
+                bool const real = m != HX_PH;
+                bool ok = false;
+                if (real && m != n) {
+                    float4 const q = a.pos_hi[m];
+                    float const ex = minimg(__fsub_rn(r1.x, q.x), a.L.x, a.invL.x);
+                    float const ey = minimg(__fsub_rn(r1.y, q.y), a.L.y, a.invL.y);
+                    float const ez = minimg(__fsub_rn(r1.z, q.z), a.L.z, a.invL.z);
+                    float const cut = typed ? a.rr_cut_skin[__float_as_uint(r1.w) * a.ntype2 + __float_as_uint(q.w)] : a.rr_cut_skin[0];
+                    ok = norm2(ex, ey, ez) <= cut;
+                }
+                unsigned const mask = __ballot_sync(0xFFFFFFFFu, ok);
+                unsigned const slot = count + __popc(mask & lane_lt);
+                count += __popc(mask);
+                if (ok && slot < a.size) {
+                    if (ROW) row[slot] = m;
+                    else row[static_cast<size_t>(slot) * a.stride] = m;
+                }
+                if (!__all_sync(0xFFFFFFFFu, real)) break;       // occupied entries sit at the front of a cell
+            }
+        }
+        if (count >= a.size) {
+            count = a.size;
+            if (lane == 0) *a.overflow = 1;
+        }
+        if (ROW) {
+            size_t const end = a.fill_all ? a.stride : min(static_cast<size_t>((count + 32u) & ~31u), a.stride);
+            for (size_t k = count + lane; k < end; k += 32) row[k] = HX_PH;
+        }
+        if (a.count_out && lane == 0) a.count_out[n] = count;
+    }
+}
+
 // ---- private rows ordered by shells of the build-time distance (see force.cu, k_force_shell) -----------------------
 struct shell_build_args {
     const unsigned* nl;
@@ -425,10 +487,7 @@ static int nlist_build_impl(const uint32_t* g_cell_dev, const unsigned ncell[3],
     cudaStream_t st = as_stream(stream);
     size_t ncells = static_cast<size_t>(ncell[0]) * ncell[1] * ncell[2];
     size_t smem = (static_cast<size_t>(27) * cell_size + NL_PAD) * (sizeof(float4) + sizeof(unsigned));
-    if (smem > 200 * 1024) {
-        set_error("hx_nlist_build: cell size %u exceeds shared memory staging capacity", cell_size);
-        return HX_E_UNSUPPORTED;
-    }
+    bool const direct = smem > 200 * 1024;      // cells too large to stage: lists straight from global memory
     nlist_args a;
     a.g_cell = g_cell_dev;
     a.pos_hi = reinterpret_cast<const float4*>(position_hi_dev);
@@ -450,7 +509,7 @@ static int nlist_build_impl(const uint32_t* g_cell_dev, const unsigned ncell[3],
     cudaError_t err;
     static std::atomic<size_t> smem_set[2] = {{0}, {0}};   // opt-in dynamic shared memory, raised on demand
     int const li = (layout == HX_LAYOUT_ROW) ? 1 : 0;
-    if (smem > 48 * 1024 && smem_set[li].load() < smem) {
+    if (!direct && smem > 48 * 1024 && smem_set[li].load() < smem) {
         err = li ? cudaFuncSetAttribute(k_nlist_build<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
                  : cudaFuncSetAttribute(k_nlist_build<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (err != cudaSuccess) {
@@ -465,9 +524,11 @@ static int nlist_build_impl(const uint32_t* g_cell_dev, const unsigned ncell[3],
             set_error("hx_nlist_build: memset: %s", cudaGetErrorString(err));
             return static_cast<int>(err);
         }
-        k_nlist_build<false><<<static_cast<unsigned>(ncells), NL_THREADS, smem, st>>>(a);
+        if (direct) k_nlist_build_direct<false><<<static_cast<unsigned>(ncells), NL_THREADS, 0, st>>>(a);
+        else k_nlist_build<false><<<static_cast<unsigned>(ncells), NL_THREADS, smem, st>>>(a);
     } else {
-        k_nlist_build<true><<<static_cast<unsigned>(ncells), NL_THREADS, smem, st>>>(a);
+        if (direct) k_nlist_build_direct<true><<<static_cast<unsigned>(ncells), NL_THREADS, 0, st>>>(a);
+        else k_nlist_build<true><<<static_cast<unsigned>(ncells), NL_THREADS, smem, st>>>(a);
     }
     return check_launch("k_nlist_build");
 }

@@ -174,10 +174,19 @@ __global__ void k_density_modes(const float4* __restrict__ pos, unsigned n, cons
             cc += s_c[w][threadIdx.x];
             ss += s_s[w][threadIdx.x];
         }
-        // (sum cos, -sum sin): density_mode.cpp:126-129
-        atomicAdd(&rho[2 * (q0 + threadIdx.x) + 0], cc);
-        atomicAdd(&rho[2 * (q0 + threadIdx.x) + 1], -ss);
+        // (sum cos, -sum sin): density_mode.cpp:126-129.  Block sums are merged as 31.32 fixed-point integers: integer
+        // addition is associative, so the result does not depend on the order in which blocks finish (|sum| <= n < 2^31;
+        // the resolution 2^-32 is far below the accuracy of a float sine); k_density_modes_finalise converts in place.
+        unsigned long long* const acc = reinterpret_cast<unsigned long long*>(rho);
+        atomicAdd(&acc[2 * (q0 + threadIdx.x) + 0], static_cast<unsigned long long>(__double2ll_rn(cc * 4294967296.0)));
+        atomicAdd(&acc[2 * (q0 + threadIdx.x) + 1], static_cast<unsigned long long>(__double2ll_rn(-ss * 4294967296.0)));
     }
+}
+
+__global__ void k_density_modes_finalise(double* __restrict__ rho, unsigned nwords)
+{
+    unsigned const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nwords) rho[i] = static_cast<double>(reinterpret_cast<long long*>(rho)[i]) * (1.0 / 4294967296.0);
 }
 
 constexpr unsigned TH_THREADS = 256;
@@ -315,7 +324,10 @@ int hx_density_modes(const hx_float4* position_hi_dev, size_t nparticle, const f
     if (bx > 296) bx = 296;
     k_density_modes<<<dim3(bx, div_up(nq, DM_QTILE)), DM_THREADS, 0, st>>>(
         reinterpret_cast<const float4*>(position_hi_dev), static_cast<unsigned>(nparticle), q_dev, nq, rho_dev);
-    return check_launch("k_density_modes");
+    int const rc = check_launch("k_density_modes");
+    if (rc) return rc;
+    k_density_modes_finalise<<<div_up(2 * static_cast<size_t>(nq), 256), 256, 0, st>>>(rho_dev, 2 * nq);
+    return check_launch("k_density_modes_finalise");
 }
 
 int hx_thermodynamics(const hx_float4* velocity_hi_dev, const float* en_pot_dev, const float* stress_dev,

@@ -252,6 +252,21 @@ def test_neighbour_lists_bit_exact(hx, oracle, dev, layout, n, rho, rc, skin, ob
     assert 40 < s["count"].mean() < 160
 
 
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("n,rho,rc,skin,ob,ol,frac", [
+    (4000, 0.8442, [2.5], 0.5, 0.04, 0.4, None),
+    (8000, 1.2, [2.5, 2.0, 2.0, 2.2], 0.3, 0.04, 0.7, 0.8),
+])
+def test_neighbour_lists_large_cells(hx, oracle, dev, layout, n, rho, rc, skin, ob, ol, frac):
+    """Cells too large for the shared-memory staging (cell_size >= 512, as the doubling of binning.cpp:216-219 produces for
+    strongly inhomogeneous systems) are served from global memory with the same list arrays."""
+    s = build_lists(hx, oracle, dev, n, rho, 27, rc, skin, ob, ol, frac, layout=layout, fill_all=1)
+    assert s["cs"] >= 512
+    assert s["flag"] == s["o_flag"] == 0
+    assert np.array_equal(s["count"], s["o_count"])
+    assert np.array_equal(s["nl"], s["o_nl"])
+
+
 def test_neighbour_lists_256k_sets(hx, oracle, dev):
     """BASELINE config 2 size, row layout without full fill: entries + terminator block."""
     s = build_lists(hx, oracle, dev, 256000, 0.8442, 22, [2.5], 0.5, 0.5, 0.4, layout=1, fill_all=0)
@@ -691,6 +706,10 @@ def test_density_modes(hx, oracle, dev):
     oracle.oracle_density_modes(support.ptr(p), C.c_size_t(n), support.ptr(q), len(q), support.ptr(o_rho))
     # per-term error of sincosf vs libm <= 2 ulp of O(1) terms; sums of n terms
     assert np.abs(rho - o_rho).max() < 4 * EPS_F * n ** 0.5 * 4
+    # block sums are merged as fixed-point integers: the result does not depend on the order in which blocks finish
+    for _ in range(5):
+        hx.check(hx.lib.hx_density_modes(dev.p(d_p), n, dev.p(d_q), len(q), dev.p(d_rho), dev.stream))
+        assert dev.down(d_rho).tobytes() == rho.tobytes()
 
 
 def test_thermodynamics(hx, oracle, dev):
