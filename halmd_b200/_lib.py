@@ -177,6 +177,9 @@ _protos = {
     "hx_ctl_reset": (C.c_int, [P, P]),
     "hx_nlist_build2": (C.c_int, [P, U3, C.c_uint, P, SZ, SZ, F3, C.c_uint, C.c_uint, F3, P, C.c_uint, SZ,
                                   C.c_int, C.c_int, P, P, P]),
+    "hx_binning_update_slab": (C.c_int, [P, SZ, F3, U3, C.c_uint, C.c_uint, C.c_uint, P, P, P, P, P]),
+    "hx_nlist_build_slab": (C.c_int, [P, U3, C.c_uint, C.c_uint, C.c_uint, P, SZ, SZ, F3, C.c_uint, C.c_uint, F3, P, C.c_uint, SZ,
+                                      C.c_int, C.c_int, P, P, P]),
     "hx_pair_force2": (C.c_int, [C.POINTER(LjParams), P, P, SZ, P, C.c_uint, SZ, C.c_int, SZ, F3, C.c_int,
                                  C.c_float, P, P, P, SZ, P, C.c_float, P]),
     "hx_verlet_finalize_integrate_range": (C.c_int, [P, P, P, P, SZ, SZ, SZ, C.c_float, F3, C.c_int, C.c_int, P, P, P]),

@@ -7,6 +7,7 @@
 // global sort: atomic slot claiming per cell (order-free) followed by a warp-local bitonic sort of
 // each cell's few entries, which restores the ascending-index order of the stable sort.
 #include "common.cuh"
+#include <algorithm>
 
 namespace hx {
 
@@ -20,9 +21,12 @@ __device__ __forceinline__ unsigned cell_coord(float r, float len, unsigned n)
     return __float2uint_rz(fma_ftz(rcp_approx(len), r, static_cast<float>(n))) % n;
 }
 
+// x0, nxl: layers of the grid in x that may hold particles (slab-decomposed ranks; 0, ncell.x otherwise): a particle
+// outside them would be missed by the kernels that visit those layers only, and raises *range_error instead
 __global__ void k_cell_claim(const float4* __restrict__ pos_hi, unsigned n, vec3 cell_len, uvec3 ncell,
                              unsigned cell_size, unsigned* __restrict__ cell_count,
-                             unsigned* __restrict__ g_cell, unsigned* __restrict__ cell_index)
+                             unsigned* __restrict__ g_cell, unsigned* __restrict__ cell_index, unsigned x0, unsigned nxl,
+                             int* __restrict__ range_error)
 {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -36,6 +40,7 @@ __global__ void k_cell_claim(const float4* __restrict__ pos_hi, unsigned n, vec3
     unsigned cz = cell_coord(p.z, cell_len.z, ncell.z);
     unsigned c = (cz * ncell.y + cy) * ncell.x + cx;
     if (cell_index) cell_index[i] = c;
+    if ((cx + ncell.x - x0) % ncell.x >= nxl) atomicOr(range_error, HX_BINNING_OUT_OF_RANGE);
     unsigned s = atomicAdd(&cell_count[c], 1u);
     if (s < cell_size) g_cell[static_cast<size_t>(c) * cell_size + s] = i;
 }
@@ -49,16 +54,21 @@ __global__ void k_device_rcp(const float* __restrict__ x, float* __restrict__ ou
 
 // one warp per cell: sort the claimed entries ascending (placeholders = 0xFFFFFFFF sort last)
 __global__ void k_cell_sort(unsigned* __restrict__ g_cell, const unsigned* __restrict__ cell_count,
-                            unsigned ncells, unsigned cell_size, unsigned pow2, int* __restrict__ overflow)
+                            unsigned ncells, unsigned cell_size, unsigned pow2, int* __restrict__ overflow, unsigned nx,
+                            unsigned x0, unsigned nxl)
 {
     extern __shared__ unsigned s_all[];
     unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     unsigned c = blockIdx.x * (blockDim.x >> 5) + warp;
     if (c >= ncells) return;
+    // the c-th cell of the visited layers [x0, x0 + nxl) (periodic) of a grid with nx layers, x fastest
+    unsigned x = x0 + c % nxl;
+    if (x >= nx) x -= nx;
+    c = (c / nxl) * nx + x;
     unsigned cnt = cell_count[c];
     if (cnt >= cell_size) {
         // binning_kernel.cu:124-127 — last placeholder occupied ⇒ overcrowded
-        if (lane == 0) *overflow = 1;
+        if (lane == 0) atomicOr(overflow, 1);       // (bit 1 may carry HX_BINNING_OUT_OF_RANGE)
         cnt = cell_size;
     }
     if (cnt < 2) return;
@@ -88,10 +98,10 @@ __global__ void k_cell_sort(unsigned* __restrict__ g_cell, const unsigned* __res
 
 using namespace hx;
 
-extern "C" int hx_binning_update(const hx_float4* position_hi_dev, size_t nparticle,
-                                 const float cell_length[3], const unsigned ncell[3], unsigned cell_size,
-                                 uint32_t* g_cell_dev, uint32_t* cell_count_dev, uint32_t* cell_index_dev,
-                                 int* overflow_flag_dev, void* stream)
+static int binning_update_impl(const hx_float4* position_hi_dev, size_t nparticle,
+                               const float cell_length[3], const unsigned ncell[3], unsigned cell_size,
+                               uint32_t* g_cell_dev, uint32_t* cell_count_dev, uint32_t* cell_index_dev,
+                               int* overflow_flag_dev, void* stream, unsigned cell_x0, unsigned cell_nx)
 {
     if (!position_hi_dev || !cell_length || !ncell || !g_cell_dev || !cell_count_dev || !overflow_flag_dev
         || cell_size == 0 || cell_size % 32 != 0) {
@@ -103,10 +113,23 @@ extern "C" int hx_binning_update(const hx_float4* position_hi_dev, size_t nparti
         set_error("hx_binning_update: cell grid out of range");
         return HX_E_INVALID;
     }
+    if (cell_nx == 0 || cell_nx > ncell[0] || cell_x0 >= ncell[0]) {
+        set_error("hx_binning_update_slab: cell layers [%u, +%u) outside the grid", cell_x0, cell_nx);
+        return HX_E_INVALID;
+    }
     cudaStream_t st = as_stream(stream);
     cudaError_t err;
-    if ((err = cudaMemsetAsync(cell_count_dev, 0, ncells * sizeof(uint32_t), st)) != cudaSuccess
-        || (err = cudaMemsetAsync(g_cell_dev, 0xFF, ncells * cell_size * sizeof(uint32_t), st)) != cudaSuccess) {
+    // counters of all cells, placeholders of the visited layers only (two strided blocks when the range wraps)
+    err = cudaMemsetAsync(cell_count_dev, 0, ncells * sizeof(uint32_t), st);
+    size_t const layer = static_cast<size_t>(cell_size) * sizeof(uint32_t), pitch = ncell[0] * layer;
+    size_t const rows = static_cast<size_t>(ncell[1]) * ncell[2];
+    unsigned const first = std::min(cell_nx, ncell[0] - cell_x0);
+    if (err == cudaSuccess && cell_nx == ncell[0]) err = cudaMemsetAsync(g_cell_dev, 0xFF, ncells * layer, st);
+    else if (err == cudaSuccess) {
+        err = cudaMemset2DAsync(reinterpret_cast<char*>(g_cell_dev) + cell_x0 * layer, pitch, 0xFF, first * layer, rows, st);
+        if (err == cudaSuccess && first < cell_nx) err = cudaMemset2DAsync(g_cell_dev, pitch, 0xFF, (cell_nx - first) * layer, rows, st);
+    }
+    if (err != cudaSuccess) {
         set_error("hx_binning_update: memset: %s", cudaGetErrorString(err));
         return static_cast<int>(err);
     }
@@ -115,7 +138,7 @@ extern "C" int hx_binning_update(const hx_float4* position_hi_dev, size_t nparti
     if (nparticle > 0) {
         k_cell_claim<<<div_up(nparticle, 256), 256, 0, st>>>(
             reinterpret_cast<const float4*>(position_hi_dev), static_cast<unsigned>(nparticle), cl, nc,
-            cell_size, cell_count_dev, g_cell_dev, cell_index_dev);
+            cell_size, cell_count_dev, g_cell_dev, cell_index_dev, cell_x0, cell_nx, overflow_flag_dev);
         int rc = check_launch("k_cell_claim");
         if (rc) return rc;
     }
@@ -127,9 +150,28 @@ extern "C" int hx_binning_update(const hx_float4* position_hi_dev, size_t nparti
         set_error("hx_binning_update: cell size %u too large", cell_size);
         return HX_E_UNSUPPORTED;
     }
-    k_cell_sort<<<div_up(ncells, warps), warps * 32, warps * pow2 * sizeof(unsigned), st>>>(
-        g_cell_dev, cell_count_dev, static_cast<unsigned>(ncells), cell_size, pow2, overflow_flag_dev);
+    size_t const visited = static_cast<size_t>(cell_nx) * rows;
+    k_cell_sort<<<div_up(visited, warps), warps * 32, warps * pow2 * sizeof(unsigned), st>>>(
+        g_cell_dev, cell_count_dev, static_cast<unsigned>(visited), cell_size, pow2, overflow_flag_dev, ncell[0], cell_x0, cell_nx);
     return check_launch("k_cell_sort");
+}
+
+extern "C" int hx_binning_update(const hx_float4* position_hi_dev, size_t nparticle,
+                                 const float cell_length[3], const unsigned ncell[3], unsigned cell_size,
+                                 uint32_t* g_cell_dev, uint32_t* cell_count_dev, uint32_t* cell_index_dev,
+                                 int* overflow_flag_dev, void* stream)
+{
+    return binning_update_impl(position_hi_dev, nparticle, cell_length, ncell, cell_size, g_cell_dev, cell_count_dev,
+                               cell_index_dev, overflow_flag_dev, stream, 0, ncell ? ncell[0] : 0);
+}
+
+extern "C" int hx_binning_update_slab(const hx_float4* position_hi_dev, size_t nparticle,
+                                      const float cell_length[3], const unsigned ncell[3], unsigned cell_size,
+                                      unsigned cell_x0, unsigned cell_nx, uint32_t* g_cell_dev, uint32_t* cell_count_dev,
+                                      uint32_t* cell_index_dev, int* overflow_flag_dev, void* stream)
+{
+    return binning_update_impl(position_hi_dev, nparticle, cell_length, ncell, cell_size, g_cell_dev, cell_count_dev,
+                               cell_index_dev, overflow_flag_dev, stream, cell_x0, cell_nx);
 }
 
 // The divisions of the path by cell and box lengths are r * MUFU.RCP(l) in the reference build (binning_kernel.cu:34-54,

@@ -28,7 +28,22 @@ struct nlist_args {
     unsigned ntype1, ntype2;
     int fill_all;
     float rr_cut_skin[HX_MAX_PAIR_TYPES];
+    // home cells served by this launch: cell_nx layers of the grid in x starting at layer cell_x0 (periodic); the whole
+    // grid for cell_x0 = 0, cell_nx = ncell.x.  A slab-decomposed rank launches blocks for its own layers only.
+    unsigned cell_x0, cell_nx;
 };
+
+// block -> home cell (x fastest, as the cell index itself)
+__device__ __forceinline__ unsigned home_cell(nlist_args const& a, unsigned block, int& cx, int& cy, int& cz)
+{
+    unsigned const xl = block % a.cell_nx, rest = block / a.cell_nx;
+    unsigned x = a.cell_x0 + xl;
+    if (x >= a.ncell.x) x -= a.ncell.x;
+    cx = static_cast<int>(x);
+    cy = static_cast<int>(rest % a.ncell.y);
+    cz = static_cast<int>(rest / a.ncell.y);
+    return (static_cast<unsigned>(cz) * a.ncell.y + static_cast<unsigned>(cy)) * a.ncell.x + x;
+}
 
 constexpr unsigned NL_THREADS = 256;
 constexpr unsigned NL_WARPS = NL_THREADS / 32;
@@ -132,17 +147,14 @@ __global__ void __launch_bounds__(NL_THREADS) k_nlist_build(nlist_args a)
     __shared__ float s_rr[HX_MAX_PAIR_TYPES];
     __shared__ float s_ext[NL_WARPS][6];
 
-    unsigned const cell = blockIdx.x;
+    int cx, cy, cz;
+    unsigned const cell = home_cell(a, blockIdx.x, cx, cy, cz);
     unsigned const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     unsigned const cs = a.cell_size;
 
     // occupied entries sit at the front of each cell (ascending index, placeholders last)
     // empty home cell, or one that holds partners only (their indices follow those of the list owners)
     if (a.g_cell[static_cast<size_t>(cell) * cs] >= a.nbuild) return;
-
-    int const cx = cell % a.ncell.x;
-    int const cy = (cell / a.ncell.x) % a.ncell.y;
-    int const cz = cell / a.ncell.x / a.ncell.y;
 
     float4* s_pos = s_dyn;                                             // [27*cs + NL_PAD] (x, y, z, species)
     unsigned* s_id = reinterpret_cast<unsigned*>(s_dyn + 27 * cs + NL_PAD);     // [27*cs + NL_PAD]
@@ -265,15 +277,13 @@ __global__ void __launch_bounds__(NL_THREADS) k_nlist_build(nlist_args a)
 template <bool ROW>
 __global__ void __launch_bounds__(NL_THREADS) k_nlist_build_direct(nlist_args a)
 {
-    unsigned const cell = blockIdx.x;
+    int cx, cy, cz;
+    unsigned const cell = home_cell(a, blockIdx.x, cx, cy, cz);
     unsigned const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     unsigned const lane_lt = (1u << lane) - 1u;
     unsigned const cs = a.cell_size;
     const unsigned* const home = a.g_cell + static_cast<size_t>(cell) * cs;
     if (home[0] >= a.nbuild) return;
-    int const cx = cell % a.ncell.x;
-    int const cy = (cell / a.ncell.x) % a.ncell.y;
-    int const cz = cell / a.ncell.x / a.ncell.y;
     bool const typed = a.ntype1 * a.ntype2 > 1;
     for (unsigned p = warp; p < cs; p += NL_WARPS) {
         unsigned const n = home[p];
@@ -457,7 +467,8 @@ static int nlist_build_impl(const uint32_t* g_cell_dev, const unsigned ncell[3],
                             const hx_float4* position_hi_dev, size_t nparticle, size_t nbuild, const float* rr_cut_skin,
                             unsigned ntype1, unsigned ntype2, const float box_length[3],
                             uint32_t* g_neighbour_dev, unsigned size, size_t stride, int layout,
-                            int fill_all, uint32_t* count_dev, int* overflow_flag_dev, void* stream)
+                            int fill_all, uint32_t* count_dev, int* overflow_flag_dev, void* stream,
+                            unsigned cell_x0 = 0, unsigned cell_nx = 0)
 {
     if (!g_cell_dev || !ncell || !position_hi_dev || !rr_cut_skin || !box_length || !g_neighbour_dev
         || !overflow_flag_dev || size == 0 || cell_size == 0 || cell_size % 32 != 0
@@ -484,8 +495,13 @@ static int nlist_build_impl(const uint32_t* g_cell_dev, const unsigned ncell[3],
         set_error("hx_nlist_build: unknown layout %d", layout);
         return HX_E_UNSUPPORTED;
     }
+    if (cell_nx == 0) { cell_x0 = 0; cell_nx = ncell[0]; }
+    if (cell_x0 >= ncell[0] || cell_nx > ncell[0]) {
+        set_error("hx_nlist_build_slab: cell layers [%u, +%u) outside the grid", cell_x0, cell_nx);
+        return HX_E_INVALID;
+    }
     cudaStream_t st = as_stream(stream);
-    size_t ncells = static_cast<size_t>(ncell[0]) * ncell[1] * ncell[2];
+    size_t ncells = static_cast<size_t>(cell_nx) * ncell[1] * ncell[2];        // home cells of this launch
     size_t smem = (static_cast<size_t>(27) * cell_size + NL_PAD) * (sizeof(float4) + sizeof(unsigned));
     bool const direct = smem > 200 * 1024;      // cells too large to stage: lists straight from global memory
     nlist_args a;
@@ -504,6 +520,8 @@ static int nlist_build_impl(const uint32_t* g_cell_dev, const unsigned ncell[3],
     a.ntype1 = ntype1;
     a.ntype2 = ntype2;
     a.fill_all = fill_all;
+    a.cell_x0 = cell_x0;
+    a.cell_nx = cell_nx;
     for (unsigned i = 0; i < HX_MAX_PAIR_TYPES; ++i) a.rr_cut_skin[i] = (i < ntype1 * ntype2) ? rr_cut_skin[i] : 0.f;
 
     cudaError_t err;
@@ -551,6 +569,18 @@ extern "C" int hx_nlist_build2(const uint32_t* g_cell_dev, const unsigned ncell[
 {
     return nlist_build_impl(g_cell_dev, ncell, cell_size, position_hi_dev, nparticle, nbuild, rr_cut_skin, ntype1, ntype2,
                             box_length, g_neighbour_dev, size, stride, layout, fill_all, count_dev, overflow_flag_dev, stream);
+}
+
+extern "C" int hx_nlist_build_slab(const uint32_t* g_cell_dev, const unsigned ncell[3], unsigned cell_size,
+                                   unsigned cell_x0, unsigned cell_nx, const hx_float4* position_hi_dev, size_t nparticle,
+                                   size_t nbuild, const float* rr_cut_skin, unsigned ntype1, unsigned ntype2,
+                                   const float box_length[3], uint32_t* g_neighbour_dev, unsigned size, size_t stride,
+                                   int layout, int fill_all, uint32_t* count_dev, int* overflow_flag_dev, void* stream)
+{
+    if (cell_nx == 0) { set_error("hx_nlist_build_slab: empty range of cell layers"); return HX_E_INVALID; }
+    return nlist_build_impl(g_cell_dev, ncell, cell_size, position_hi_dev, nparticle, nbuild, rr_cut_skin, ntype1, ntype2,
+                            box_length, g_neighbour_dev, size, stride, layout, fill_all, count_dev, overflow_flag_dev, stream,
+                            cell_x0, cell_nx);
 }
 
 extern "C" int hx_shell_rows_plan(float skin, hx_shell_rows* shells)

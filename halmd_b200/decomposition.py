@@ -53,6 +53,19 @@ class SlabDecomposition:
             elif float(self.width) < float(self.halo):
                 raise ValueError("slab width below r_c + skin: use fewer ranks")
 
+    def cell_layers(self, cell_length, ncell_x):
+        """Layers of the global cell grid in x that can hold this rank's particles (owned and ghosts): first layer and
+        count, periodic.  The cell of x is uint(x / l + n) % n (csrc/binning.cu); one layer of margin on either side
+        covers the rounding of that quotient and of the slab faces."""
+        if self.nranks == 1:
+            return 0, int(ncell_x)
+        a = int(math.floor((float(self.lo) - float(self.halo)) / cell_length + ncell_x)) - 1
+        b = int(math.floor((float(self.hi) + float(self.halo)) / cell_length + ncell_x)) + 1
+        count = b - a + 1
+        if count >= ncell_x:
+            return 0, int(ncell_x)
+        return a % int(ncell_x), count
+
     def slab_of(self, x):
         """Owner slab of wrapped coordinates x (float32), as k_dd_owner_keys computes it."""
         x = np.asarray(x, dtype=np.float32)
@@ -291,6 +304,7 @@ class DecomposedSystem:
         if min(ncell) < 3:
             raise hx.HxError("neighbour: number of cells per dimension must be at least 3")
         self.ncells = int(np.prod(list(ncell)))
+        self.cell_x0, self.cell_nx = self.dec.cell_layers(float(cl[0]), int(ncell[0]))
         size = C.c_uint()
         hx.check(self.lib.hx_nlist_plan(self.r_cut_max, float(skin), self.n_global, float(np.prod(self.L)), occ_n, self.cell_size, C.byref(size)))
         self.occ_n = occ_n
@@ -336,7 +350,9 @@ class DecomposedSystem:
         self.counts = z(4, dtype=i32)
         self.ctl = z(4, dtype=i32)
         self.flags = z(4, dtype=i32)
-        self.g_cell = torch.empty(self.ncells * self.cell_size, dtype=i32, device=dev)
+        # placeholders everywhere, once: list updates rewrite this slab's layers only (hx_binning_update_slab), and no
+        # particle of this rank ever maps outside them (checked on the device)
+        self.g_cell = torch.full((self.ncells * self.cell_size,), -1, dtype=i32, device=dev)
         self.cell_count = z(self.ncells, dtype=i32)
         self.nl = torch.empty(self.own_cap * self.stride, dtype=i32, device=dev)
         self.nl_count = z(self.own_cap, dtype=i32)
@@ -612,21 +628,26 @@ class DecomposedSystem:
         ntot = self.n_own + self.n_ghost
         while True:
             self.flags.zero_()
-            hx.check(self.lib.hx_binning_update(self._p(self.pos), ntot, self.cell_length, self.ncell, self.cell_size, self._p(self.g_cell),
-                                                self._p(self.cell_count), None, self._p(self.flags), self.st), "binning")
-            hx.check(self.lib.hx_nlist_build2(self._p(self.g_cell), self.ncell, self.cell_size, self._p(self.pos), ntot, self.n_own,
-                                              self.rr_cut_skin, self.nt, self.nt, self.Lf, self._p(self.nl), self.size, self.stride,
-                                              hx.LAYOUT_ROW, 0, self._p(self.nl_count), self._p(self.flags, 1), self.st), "nlist")
+            # placeholders, cell sorts and list blocks for this slab's layers of the global grid only
+            hx.check(self.lib.hx_binning_update_slab(self._p(self.pos), ntot, self.cell_length, self.ncell, self.cell_size,
+                                                     self.cell_x0, self.cell_nx, self._p(self.g_cell), self._p(self.cell_count), None,
+                                                     self._p(self.flags), self.st), "binning")
+            hx.check(self.lib.hx_nlist_build_slab(self._p(self.g_cell), self.ncell, self.cell_size, self.cell_x0, self.cell_nx,
+                                                  self._p(self.pos), ntot, self.n_own, self.rr_cut_skin, self.nt, self.nt, self.Lf,
+                                                  self._p(self.nl), self.size, self.stride, hx.LAYOUT_ROW, 0, self._p(self.nl_count),
+                                                  self._p(self.flags, 1), self.st), "nlist")
             hx.check(self.lib.hx_count_max(self._p(self.nl_count), self.n_own, self._p(self.flags, 2), self.st), "count_max")
             # every rank must take the same decision: the cell grid and list size are global properties (and the longest
             # list, which sizes the private shell rows, may as well be); one reduction, one host read
             self.ex.allreduce(self.flags, "max")
             f0, f1, self.longest_list = (int(v) for v in self.flags.cpu().numpy()[:3])
             self.stats["syncs"] += 1
+            if f0 & 2:
+                raise hx.HxError(f"rank {self.rank}: a particle lies outside the cell layers [{self.cell_x0}, +{self.cell_nx}) of its slab")
             if f0:
                 # binning.cpp:216-219 — overcrowded cells: double the cell size
                 self.cell_size *= 2
-                self.g_cell = torch.empty(self.ncells * self.cell_size, dtype=torch.int32, device=self.pos.device)
+                self.g_cell = torch.full((self.ncells * self.cell_size,), -1, dtype=torch.int32, device=self.pos.device)
                 continue
             if f1:
                 # from_binning.cpp:277-280 — overcrowded lists: halve the occupancy

@@ -437,6 +437,20 @@ int hx_nlist_build2(const uint32_t* g_cell_dev, const unsigned ncell[3], unsigne
                     unsigned ntype1, unsigned ntype2, const float box_length[3], uint32_t* g_neighbour_dev,
                     unsigned size, size_t stride, int layout, int fill_all, uint32_t* count_dev,
                     int* overflow_flag_dev, void* stream);
+/* Slab-decomposed ranks hold particles in a few layers of the (global) cell grid only: cell_nx layers in x starting
+ * at layer cell_x0 (periodic).  These variants place placeholders, sort cells and launch list blocks for those layers
+ * only — work per rank proportional to its own particles, not to the global grid.  A particle outside the layers sets
+ * *overflow_flag_dev to HX_BINNING_OUT_OF_RANGE in hx_binning_update_slab (the caller's layer arithmetic is wrong). */
+#define HX_BINNING_OUT_OF_RANGE 2
+int hx_binning_update_slab(const hx_float4* position_hi_dev, size_t nparticle, const float cell_length[3],
+                           const unsigned ncell[3], unsigned cell_size, unsigned cell_x0, unsigned cell_nx,
+                           uint32_t* g_cell_dev, uint32_t* cell_count_dev, uint32_t* cell_index_dev,
+                           int* overflow_flag_dev, void* stream);
+int hx_nlist_build_slab(const uint32_t* g_cell_dev, const unsigned ncell[3], unsigned cell_size, unsigned cell_x0,
+                        unsigned cell_nx, const hx_float4* position_hi_dev, size_t nparticle, size_t nbuild,
+                        const float* rr_cut_skin, unsigned ntype1, unsigned ntype2, const float box_length[3],
+                        uint32_t* g_neighbour_dev, unsigned size, size_t stride, int layout, int fill_all,
+                        uint32_t* count_dev, int* overflow_flag_dev, void* stream);
 int hx_pair_force2(const hx_lj_params* potential, const hx_float4* position1_hi_dev,
                    const hx_float4* position2_hi_dev, size_t nparticle2, const uint32_t* g_neighbour_dev,
                    unsigned size, size_t stride, int layout, size_t nparticle, const float box_length[3],

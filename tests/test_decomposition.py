@@ -65,6 +65,33 @@ def test_slab_ownership_partitions_the_box():
                 assert np.any(key == 3)
 
 
+def test_cell_layers_cover_the_slab_and_its_halo():
+    """SlabDecomposition.cell_layers: every position a rank can hold (its slab widened by the halo, wrapped into the
+    box) falls into the layers of the global cell grid the rank processes, with a layer to spare on either side — also
+    with the cell index evaluated one ulp off, as the device's approximate reciprocal may (csrc/binning.cu cell_coord)."""
+    from halmd_b200.decomposition import SlabDecomposition
+    rng = np.random.default_rng(3)
+    for Lx, P, halo in ((423.2, 8, 3.0), (120.0, 4, 3.0), (60.0, 2, 3.0), (37.1, 3, 2.8), (30.0, 8, 3.0), (19.0, 2, 3.0), (64.3, 1, 3.0)):
+        n = int(Lx // halo)
+        ell = Lx / n
+        for r in range(P):
+            d = SlabDecomposition([Lx, 20.0, 20.0], P, r, halo)
+            x0, nx = d.cell_layers(np.float32(ell), n)
+            assert 0 <= x0 < n and 1 <= nx <= n
+            x = rng.uniform(float(d.lo) - float(d.halo), float(d.hi) + float(d.halo), 200000)
+            x = np.concatenate([x, [float(d.lo) - float(d.halo), float(d.hi) + float(d.halo), float(d.lo), float(d.hi)]])
+            x = (x - np.rint(x / Lx) * Lx).astype(np.float32)
+            for rcp in (np.float32(1) / np.float32(ell), np.nextafter(np.float32(1) / np.float32(ell), np.float32(2)),
+                        np.nextafter(np.float32(1) / np.float32(ell), np.float32(0))):
+                c = np.floor(x.astype(np.float64) * float(rcp) + n).astype(np.int64) % n
+                rel = (c - x0) % n
+                assert rel.max() < nx, (Lx, P, r)
+                if nx < n:
+                    assert rel.min() >= 1 and rel.max() <= nx - 2       # the margin layers stay empty
+        if P >= 4 and Lx / P > 6 * halo:
+            assert nx < n                                               # a slab processes a fraction of the grid
+
+
 def test_slab_rejects_thin_slabs():
     from halmd_b200.decomposition import SlabDecomposition
     with pytest.raises(ValueError):
