@@ -184,7 +184,7 @@ _protos = {
                                  C.c_float, P, P, P, SZ, P, C.c_float, P]),
     "hx_verlet_finalize_integrate_range": (C.c_int, [P, P, P, P, SZ, SZ, SZ, C.c_float, F3, C.c_int, C.c_int, P, P, P]),
     "hx_dd_owner_keys": (C.c_int, [P, SZ, C.c_float, C.c_float, C.c_int, C.c_int, P, P, P]),
-    "hx_dd_ghost_keys": (C.c_int, [P, SZ, C.c_float, C.c_float, C.c_float, C.c_int, P, P, P]),
+    "hx_dd_ghost_keys": (C.c_int, [P, SZ, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, P, P, P]),
     "hx_dd_permute": (C.c_int, [P, SZ, SZ, P, P, P, P, P, P, P, P, P]),
     "hx_gather_float4": (C.c_int, [P, P, SZ, P, P, P]),
     "hx_gather_u32": (C.c_int, [P, P, SZ, P, P]),

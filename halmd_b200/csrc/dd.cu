@@ -43,14 +43,20 @@ __global__ void k_dd_owner_keys(const float4* __restrict__ pos_hi, unsigned n, f
 }
 
 // key 0: within `halo` of the slab face(s) on the given side (0: low face, 1: high face, 2: either), else 1
+// Owned particles lie in [lo, hi) up to a period of the box: the integrator leaves coordinates in [-L/2, +L/2], and a
+// particle at +L/2 belongs to the slab that starts at -L/2 (slab_of folds it).  The distances to the faces are folded
+// the same way, or that particle would be sent to the wrong neighbour and missed by the right one.
 __global__ void k_dd_ghost_keys(const float4* __restrict__ pos_hi, unsigned n, float lo, float hi, float halo, int side,
-                                unsigned* __restrict__ keys, unsigned* __restrict__ count)
+                                float box_length_x, unsigned* __restrict__ keys, unsigned* __restrict__ count)
 {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     bool sel = false;
     if (i < n) {
         float x = pos_hi[i].x;
-        bool near_lo = __fsub_rn(x, lo) < halo, near_hi = __fsub_rn(hi, x) < halo;
+        float d_lo = __fsub_rn(x, lo), d_hi = __fsub_rn(hi, x);
+        if (d_hi < 0.f) { d_lo = __fsub_rn(d_lo, box_length_x); d_hi = __fadd_rn(d_hi, box_length_x); }
+        else if (d_lo < 0.f) { d_lo = __fadd_rn(d_lo, box_length_x); d_hi = __fsub_rn(d_hi, box_length_x); }
+        bool near_lo = d_lo < halo, near_hi = d_hi < halo;
         sel = side == 0 ? near_lo : (side == 1 ? near_hi : (near_lo || near_hi));
         keys[i] = sel ? 0u : 1u;
     }
@@ -165,9 +171,9 @@ int hx_dd_owner_keys(const hx_float4* position_hi_dev, size_t nparticle, float x
 }
 
 int hx_dd_ghost_keys(const hx_float4* position_hi_dev, size_t nparticle, float lo, float hi, float halo, int side,
-                     uint32_t* keys_dev, uint32_t* count_dev /*1, zeroed here*/, void* stream)
+                     float box_length_x, uint32_t* keys_dev, uint32_t* count_dev /*1, zeroed here*/, void* stream)
 {
-    if (!position_hi_dev || !keys_dev || !count_dev || side < 0 || side > 2 || nparticle >= 0x7FFFFFFFull) {
+    if (!position_hi_dev || !keys_dev || !count_dev || side < 0 || side > 2 || nparticle >= 0x7FFFFFFFull || !(box_length_x > 0)) {
         set_error("hx_dd_ghost_keys: invalid argument");
         return HX_E_INVALID;
     }
@@ -176,7 +182,7 @@ int hx_dd_ghost_keys(const hx_float4* position_hi_dev, size_t nparticle, float l
     if (err != cudaSuccess) { set_error("hx_dd_ghost_keys: %s", cudaGetErrorString(err)); return static_cast<int>(err); }
     if (nparticle == 0) return HX_OK;
     k_dd_ghost_keys<<<div_up(nparticle, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(position_hi_dev),
-                                                          static_cast<unsigned>(nparticle), lo, hi, halo, side, keys_dev, count_dev);
+                                                          static_cast<unsigned>(nparticle), lo, hi, halo, side, box_length_x, keys_dev, count_dev);
     return check_launch("k_dd_ghost_keys");
 }
 

@@ -86,8 +86,14 @@ class SlabDecomposition:
     def ghost_mask(self, x, side):
         """Particles within the halo of the low (0), high (1) or either (2) face."""
         x = np.asarray(x, dtype=np.float32)
-        near_lo = (x - self.lo) < self.halo
-        near_hi = (self.hi - x) < self.halo
+        # distances to the faces modulo the box length, as k_dd_ghost_keys folds them: a coordinate of +L/2 belongs to
+        # the slab that starts at -L/2
+        Lx = np.float32(self.L[0])
+        d_lo, d_hi = x - self.lo, self.hi - x
+        up, down = d_hi < 0, (d_hi >= 0) & (d_lo < 0)
+        d_lo = np.where(up, d_lo - Lx, np.where(down, d_lo + Lx, d_lo)).astype(np.float32)
+        d_hi = np.where(up, d_hi + Lx, np.where(down, d_hi - Lx, d_hi)).astype(np.float32)
+        near_lo, near_hi = d_lo < self.halo, d_hi < self.halo
         return near_lo if side == 0 else (near_hi if side == 1 else (near_lo | near_hi))
 
     def ghost_sides(self):
@@ -570,7 +576,7 @@ class DecomposedSystem:
             self.send_buf[dest] = torch.zeros(0, 4, dtype=torch.float32, device=self.pos.device)
         for side, dest in dec.ghost_sides():
             hx.check(self.lib.hx_dd_ghost_keys(self._p(self.pos), n, float(dec.lo), float(dec.hi), float(dec.halo), side,
-                                               self._p(self.keys), self._p(self.counts), self.st), "ghost_keys")
+                                               float(np.float32(self.L[0])), self._p(self.keys), self._p(self.counts), self.st), "ghost_keys")
             self._sort_pairs(n, 8)
             m = int(self.counts[0].item())
             self.stats["syncs"] += 1

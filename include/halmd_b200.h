@@ -466,12 +466,13 @@ int hx_verlet_finalize_integrate_range(hx_float4* position_dev, hx_float4* image
  * Rank r of nranks owns wrapped x in [x0 + r*width, x0 + (r+1)*width).  Selections are produced as small integer
  * keys for hx_sort_pairs_stable_u32 so that migrants and ghosts keep their memory order (deterministic).
  * hx_dd_owner_keys: 0 stays, 1 to rank-1, 2 to rank+1 (1 for both when nranks == 2), 3 lost; counts_dev[4] histogram.
- * hx_dd_ghost_keys: 0 if within `halo` of the low (side 0), high (side 1) or either (side 2) face, else 1.
+ * hx_dd_ghost_keys: 0 if within `halo` of the low (side 0), high (side 1) or either (side 2) face, else 1; the distances to the
+ * faces are taken modulo box_length_x (a coordinate of +L/2 belongs to the slab that starts at -L/2).
  * hx_dd_permute: out[i] = in[index[i]], i < nparticle, for position/velocity (hi and lo planes), image and id. */
 int hx_dd_owner_keys(const hx_float4* position_hi_dev, size_t nparticle, float x0, float width, int nranks, int rank,
                      uint32_t* keys_dev, uint32_t* counts_dev, void* stream);
 int hx_dd_ghost_keys(const hx_float4* position_hi_dev, size_t nparticle, float lo, float hi, float halo, int side,
-                     uint32_t* keys_dev, uint32_t* count_dev, void* stream);
+                     float box_length_x, uint32_t* keys_dev, uint32_t* count_dev, void* stream);
 int hx_dd_permute(const uint32_t* index_dev, size_t nparticle, size_t array_size, const hx_float4* position_in_dev,
                   hx_float4* position_out_dev, const hx_float4* velocity_in_dev, hx_float4* velocity_out_dev,
                   const hx_float4* image_in_dev, hx_float4* image_out_dev, const uint32_t* id_in_dev,

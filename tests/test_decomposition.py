@@ -92,6 +92,24 @@ def test_cell_layers_cover_the_slab_and_its_halo():
             assert nx < n                                               # a slab processes a fraction of the grid
 
 
+def test_ghost_selection_folds_the_periodic_image():
+    """A coordinate of exactly +L/2 (the integrator's wrap leaves [-L/2, +L/2]) is owned by the slab that starts at -L/2;
+    it must be offered to that slab's LEFT neighbour (the last rank) and not to the right one."""
+    from halmd_b200.decomposition import SlabDecomposition
+    L = [96.0, 10.0, 10.0]
+    x = np.array([48.0, -48.0, -47.0, -42.0, -36.5, 47.9], dtype=np.float32)
+    d0 = SlabDecomposition(L, 8, 0, 3.0)
+    assert np.array_equal(d0.slab_of(x), [0, 0, 0, 0, 0, 7])
+    own = x[:5]
+    assert np.array_equal(d0.ghost_mask(own, 0), [True, True, True, False, False])        # towards rank 7
+    assert np.array_equal(d0.ghost_mask(own, 1), [False, False, False, False, True])       # towards rank 1
+    d7 = SlabDecomposition(L, 8, 7, 3.0)
+    assert np.array_equal(d7.ghost_mask(x[5:], 1), [True]) and np.array_equal(d7.ghost_mask(x[5:], 0), [False])
+    # two ranks: the single combined list holds every boundary particle once
+    d = SlabDecomposition(L, 2, 0, 3.0)
+    assert np.array_equal(d.ghost_mask(np.array([48.0, -48.0, -1.0, -24.0], dtype=np.float32), 2), [True, True, True, False])
+
+
 def test_slab_rejects_thin_slabs():
     from halmd_b200.decomposition import SlabDecomposition
     with pytest.raises(ValueError):
