@@ -54,8 +54,10 @@ __global__ void k_dd_ghost_keys(const float4* __restrict__ pos_hi, unsigned n, f
     if (i < n) {
         float x = pos_hi[i].x;
         float d_lo = __fsub_rn(x, lo), d_hi = __fsub_rn(hi, x);
-        if (d_hi < 0.f) { d_lo = __fsub_rn(d_lo, box_length_x); d_hi = __fadd_rn(d_hi, box_length_x); }
-        else if (d_lo < 0.f) { d_lo = __fadd_rn(d_lo, box_length_x); d_hi = __fsub_rn(d_hi, box_length_x); }
+        // (a period away, not a rounding error of the face coordinates: owned particles may sit an ulp outside [lo, hi))
+        float const half = 0.5f * box_length_x;
+        if (d_lo > half) { d_lo = __fsub_rn(d_lo, box_length_x); d_hi = __fadd_rn(d_hi, box_length_x); }
+        else if (d_hi > half) { d_lo = __fadd_rn(d_lo, box_length_x); d_hi = __fsub_rn(d_hi, box_length_x); }
         bool near_lo = d_lo < halo, near_hi = d_hi < halo;
         sel = side == 0 ? near_lo : (side == 1 ? near_hi : (near_lo || near_hi));
         keys[i] = sel ? 0u : 1u;

@@ -90,7 +90,9 @@ class SlabDecomposition:
         # the slab that starts at -L/2
         Lx = np.float32(self.L[0])
         d_lo, d_hi = x - self.lo, self.hi - x
-        up, down = d_hi < 0, (d_hi >= 0) & (d_lo < 0)
+        half = np.float32(0.5) * Lx          # a period away — not a rounding error of the face coordinates
+        up = d_lo > half
+        down = ~up & (d_hi > half)
         d_lo = np.where(up, d_lo - Lx, np.where(down, d_lo + Lx, d_lo)).astype(np.float32)
         d_hi = np.where(up, d_hi + Lx, np.where(down, d_hi - Lx, d_hi)).astype(np.float32)
         near_lo, near_hi = d_lo < self.halo, d_hi < self.halo
@@ -649,7 +651,14 @@ class DecomposedSystem:
             f0, f1, self.longest_list = (int(v) for v in self.flags.cpu().numpy()[:3])
             self.stats["syncs"] += 1
             if f0 & 2:
-                raise hx.HxError(f"rank {self.rank}: a particle lies outside the cell layers [{self.cell_x0}, +{self.cell_nx}) of its slab")
+                # a particle outside the layers computed for this slab (never expected): report it and bin the whole grid
+                # from now on — the layers are an optimisation, the global grid is always correct
+                if self.cell_nx >= int(self.ncell[0]):
+                    raise hx.HxError(f"rank {self.rank}: cell index outside the global grid")
+                self._report_outside_layers(ntot)
+                self.cell_x0, self.cell_nx = 0, int(self.ncell[0])
+                self.stats["layer_fallbacks"] = self.stats.get("layer_fallbacks", 0) + 1
+                continue
             if f0:
                 # binning.cpp:216-219 — overcrowded cells: double the cell size
                 self.cell_size *= 2
@@ -666,6 +675,17 @@ class DecomposedSystem:
                 self.nl = torch.empty(self.own_cap * self.stride, dtype=torch.int32, device=self.pos.device)
                 continue
             break
+
+    def _report_outside_layers(self, ntot):
+        import sys
+        x = self.pos[:ntot, 0].float().cpu().numpy()
+        ell, nx = float(self.cell_length[0]), int(self.ncell[0])
+        c = np.floor(x.astype(np.float64) / ell + nx).astype(np.int64) % nx
+        bad = np.nonzero((c - self.cell_x0) % nx >= self.cell_nx)[0]
+        if len(bad):
+            print(f"halmd_b200: rank {self.rank}: {len(bad)} particle(s) outside the cell layers [{self.cell_x0}, +{self.cell_nx}) of the "
+                  f"slab [{float(self.dec.lo)}, {float(self.dec.hi)}): index {bad[:4].tolist()} (owned below {self.n_own}), "
+                  f"x = {x[bad[:4]].tolist()}; binning the whole grid from now on", file=sys.stderr, flush=True)
 
     def update_lists(self):
         """neighbour update: on_prepend_update (migration + sort) -> binning -> lists -> displacement zero."""

@@ -105,6 +105,10 @@ def test_ghost_selection_folds_the_periodic_image():
     assert np.array_equal(d0.ghost_mask(own, 1), [False, False, False, False, True])       # towards rank 1
     d7 = SlabDecomposition(L, 8, 7, 3.0)
     assert np.array_equal(d7.ghost_mask(x[5:], 1), [True]) and np.array_equal(d7.ghost_mask(x[5:], 0), [False])
+    # a particle an ulp below its slab's low face (rounding of lo = x0 + rank * width) still goes to the left neighbour
+    d5 = SlabDecomposition([423.2317, 10.0, 10.0], 8, 5, 3.0)
+    xb = np.array([np.nextafter(d5.lo, np.float32(-1e9)), d5.lo, np.nextafter(d5.hi, np.float32(-1e9))], dtype=np.float32)
+    assert np.array_equal(d5.ghost_mask(xb, 0), [True, True, False]) and np.array_equal(d5.ghost_mask(xb, 1), [False, False, True])
     # two ranks: the single combined list holds every boundary particle once
     d = SlabDecomposition(L, 2, 0, 3.0)
     assert np.array_equal(d.ghost_mask(np.array([48.0, -48.0, -1.0, -24.0], dtype=np.float32), 2), [True, True, True, False])
