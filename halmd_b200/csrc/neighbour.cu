@@ -438,8 +438,13 @@ __global__ void __launch_bounds__(SB_WARPS * 32) k_shell_rows(shell_build_args a
             dst[shell_row_offset(s_cnt[w][sh * SB_SLOTS + slot] + rank)] = s_j[w][k];
         }
     }
-    // the rest of the row holds the particle's own index: safe to gather, masked by its position
-    for (unsigned k = cnt + lane; k < a.pitch; k += 32) dst[shell_row_offset(k)] = i;
+    // behind its entries the row holds the particle's own index — safe to gather, masked by its position — as far as
+    // the force kernel walks the rows of this tile of 8 particles: up to the longest of them, in steps of 16 entries
+    unsigned const tile = i & ~7u;
+    unsigned longest = (lane < 8u && tile + lane < a.n) ? min(a.count[tile + lane], SB_MAX) : 0u;
+    longest = __reduce_max_sync(0xFFFFFFFFu, longest);
+    unsigned const fill_end = min((longest + 15u) & ~15u, a.pitch);
+    for (unsigned k = cnt + lane; k < fill_end; k += 32) dst[shell_row_offset(k)] = i;
     if (lane == 0)
         a.ends[i] = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
     // rows of a last, incomplete tile and the slack behind it (read ahead by the force kernel, never used)
