@@ -171,15 +171,11 @@ def close(f, g, n, tol):
     return rel
 
 
-@pytest.mark.parametrize("n", [16000, 15997])
-@pytest.mark.parametrize("trunc", [0, 1, 2, 3])
-@pytest.mark.parametrize("dmax", [0.0, 0.03, 0.12, 0.249])
+@pytest.mark.parametrize("n,trunc,dmax", [(16000, t, d) for d in (0.0, 0.03, 0.12, 0.249) for t in (0, 1, 2, 3)] + [(15997, 2, 0.12)])
 def test_shell_force_equals_full_walk(hx, oracle, dev, n, trunc, dmax):
     """Lists built at r0, positions moved by up to dmax: the prefix walk must not lose a pair inside the cutoff
     (same forces as the full walk up to the order of the compensated sums) and match the oracle.  n = 15997: the last
-    tile of 8 particles is incomplete."""
-    if n != 16000 and (trunc != 2 or dmax not in (0.12,)):
-        pytest.skip("the incomplete last tile is exercised for smooth_r4 at one displacement")
+    tile of 8 particles is incomplete (exercised for smooth_r4 at one displacement)."""
     skin = 0.5
     lanes = 4
     s = build_lists(hx, oracle, dev, n, 0.8442, 73, [2.5], skin, 0.5, 0.4, layout=1, fill_all=0, reduce=True)
