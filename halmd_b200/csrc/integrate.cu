@@ -41,7 +41,10 @@ __device__ __forceinline__ float4 ld_ordered(const float4* p)
 // positions in the decomposed loop, whose ghost slots the neighbour ranks fill over NVLink while this rank's force kernel
 // may still read the old buffer (dd.cu).  All loads of pos precede the stores, so the two may alias.
 template <bool FINALIZE, bool INTEGRATE>
-__global__ void __launch_bounds__(128) k_verlet(const float4* pos, float4* pos_out, float4* __restrict__ image,
+#ifndef V_THREADS_N
+#define V_THREADS_N 128
+#endif
+__global__ void __launch_bounds__(V_THREADS_N) k_verlet(const float4* pos, float4* pos_out, float4* __restrict__ image,
                                                float4* __restrict__ vel, const float4* __restrict__ force,
                                                unsigned n, unsigned nproc, unsigned A, float dt, vec3 L, vec3 invL,
                                                const float4* __restrict__ r0, unsigned* __restrict__ ctl)
@@ -433,7 +436,7 @@ int verlet_launch(bool fin, bool integ, hx_float4* pos, hx_float4* image, hx_flo
         Lv = make_vec3(L);
         iLv = {1.0f / L[0], 1.0f / L[1], 1.0f / L[2]};
     }
-    dim3 grid(div_up(nproc > 0 ? nproc : 1, 128)), block(128);
+    dim3 grid(div_up(nproc > 0 ? nproc : 1, V_THREADS_N)), block(V_THREADS_N);
     cudaStream_t st = as_stream(stream);
     float4* p = reinterpret_cast<float4*>(pos);
     float4* po = reinterpret_cast<float4*>(pos_out_arg ? pos_out_arg : pos);
