@@ -558,7 +558,7 @@ struct hxm_core {
             p->reduced = true;      // the integration kernel reduces every position before the force kernel reads it
             // NVE with private shell rows and no further force contributions: all steps of the chunk but the first
             // integrate in the tail of the force kernel of the step before (one launch per step)
-            bool const chain = fuse && fused_verlet && chunk > 1 && f->walls.empty() && nb->shells_valid
+            bool const chain = fuse && fused_verlet && p->pos_c && chunk > 1 && f->walls.empty() && nb->shells_valid
                                && nb->shell_potential == &f->potential->p;
             if (chain) {
                 HXM_TRY(hx_verlet_finalize_integrate(
@@ -843,7 +843,6 @@ int hxm_particle_create(size_t nparticle, unsigned nspecies, void* stream, hxm_p
     size_t A = p->A;
     HXM_TRY(dev_alloc(&p->pos, 2 * A)); HXM_TRY(dev_alloc(&p->vel, 2 * A)); HXM_TRY(dev_alloc(&p->image, A));
     HXM_TRY(dev_alloc(&p->force, A)); HXM_TRY(dev_alloc(&p->pos_b, 2 * A)); HXM_TRY(dev_alloc(&p->vel_b, 2 * A));
-    HXM_TRY(dev_alloc(&p->pos_c, 2 * A));
     HXM_TRY(dev_alloc(&p->image_b, A)); HXM_TRY(dev_alloc(&p->en_pot, A)); HXM_TRY(dev_alloc(&p->stress, 6 * A));
     HXM_TRY(dev_alloc(&p->id, A)); HXM_TRY(dev_alloc(&p->rid, A)); HXM_TRY(dev_alloc(&p->id_b, A));
     HXM_TRY(hx_state_init(reinterpret_cast<hx_float4*>(p->pos), reinterpret_cast<hx_float4*>(p->vel),
@@ -851,8 +850,6 @@ int hxm_particle_create(size_t nparticle, unsigned nspecies, void* stream, hxm_p
                           p->n, A, p->st));
     HXM_CUDA(cudaMemsetAsync(p->en_pot, 0, A * sizeof(float), p->st));
     HXM_CUDA(cudaMemsetAsync(p->stress, 0, 6 * A * sizeof(float), p->st));
-    // (the padding entries behind nparticle are never written again: both buffers of the fused chain hold the initial values)
-    HXM_CUDA(cudaMemcpyAsync(p->pos_c, p->pos, 2 * A * sizeof(float4), cudaMemcpyDeviceToDevice, p->st));
     HXM_CUDA(cudaStreamSynchronize(p->st));
     *out = p.release();
     return 0;
@@ -1401,6 +1398,13 @@ int hxm_core_set_chunk(hxm_core* c, unsigned min_chunk, unsigned max_chunk)
 int hxm_core_set_fused_verlet(hxm_core* c, int enable)
 {
     if (!c) return HX_E_INVALID;
+    hxm_particle* p = c->integrator->particle;
+    if (enable && !p->pos_c) {
+        // second position buffer of the chain, allocated on first use; the padding entries behind nparticle are never
+        // written by the kernels, so both buffers hold the same values there
+        HXM_TRY(dev_alloc(&p->pos_c, 2 * p->A));
+        HXM_CUDA(cudaMemcpyAsync(p->pos_c, p->pos, 2 * p->A * sizeof(float4), cudaMemcpyDeviceToDevice, p->st));
+    }
     c->fused_verlet = enable != 0;
     return 0;
 }
