@@ -16,7 +16,7 @@ for k in k_force_shell:1500 k_nlist_build:40 k_shell_rows:40 k_verlet:900; do
         -f -o $out/${tag}_$name $B > $out/${tag}_${name}_ncu.log 2>&1
 done
 B3="python bench.py --config cfg3 --steps 1 --warmup 1 --md-steps 200 --melt-steps 200 --no-cpu-baseline --no-extra"
-for k in k_density_modes:1 k_andersen_plan:300 k_andersen_apply:300 k_msd_partial:0; do
+for k in k_density_modes:1; do
     name=${k%%:*}; skip=${k##*:}
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$name -s $skip -c 1 \
         -f -o $out/${tag}_$name $B3 > $out/${tag}_${name}_ncu.log 2>&1
