@@ -552,8 +552,9 @@ def run_ours(args, cfg):
         st0 = s.dd.download()
         pos_h, vel_h = st0["position"], st0["velocity"]
     else:
-        pos_h = s.particle.get("position_ds")
-        vel_h = s.particle.get("velocity_ds")
+        # host buffers of the end-to-end leg in pinned memory (the samples a caller keeps between blocks)
+        pos_h = s.particle.get("position_ds", out=torch.empty(s.particle.nparticle, 3, dtype=torch.float64).pin_memory().numpy())
+        vel_h = s.particle.get("velocity_ds", out=torch.empty(s.particle.nparticle, 3, dtype=torch.float64).pin_memory().numpy())
     h2d = pos_h.nbytes + vel_h.nbytes
     d2h = pos_h.nbytes + vel_h.nbytes + 10 * 8
     e2e_times = []
@@ -570,8 +571,8 @@ def run_ours(args, cfg):
             s.particle.set("position_ds", pos_h)
             s.particle.set("velocity_ds", vel_h)
             s.run(md)
-            pos_h = s.particle.get("position_ds")
-            vel_h = s.particle.get("velocity_ds")
+            s.particle.get("position_ds", out=pos_h)
+            s.particle.get("velocity_ds", out=vel_h)
         th = s.thermodynamics()
         torch.cuda.synchronize()
         if i >= 2:

@@ -105,9 +105,14 @@ class particle(_Handle):
         dtype, ncomp = self._arrays[name]
         return dtype, (self.nparticle, ncomp) if ncomp else (self.nparticle,)
 
-    def get(self, name):
+    def get(self, name, out=None):
+        """Host copy of a particle array; `out` (C-contiguous, right dtype and shape — e.g. a view of pinned memory, which
+        lets the device-to-host copy run at the full PCIe rate) is filled and returned when given."""
         dtype, shape = self._shape(name)
-        out = np.zeros(shape, dtype=dtype)
+        if out is None:
+            out = np.zeros(shape, dtype=dtype)
+        elif out.dtype != dtype or out.shape != shape or not out.flags["C_CONTIGUOUS"]:
+            raise HxError(f"particle.get('{name}'): out must be a C-contiguous {np.dtype(dtype).name} array of shape {shape}")
         check(lib.hxm_particle_get(self._h, name.encode(), out.ctypes.data_as(C.c_void_p)), f"particle.get('{name}')")
         return out
 
