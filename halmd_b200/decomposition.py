@@ -400,6 +400,8 @@ class DecomposedSystem:
         self.use_shells = True
         self._staging = {}
         self.shells, self.shell_rows, self.shell_ends = None, None, None
+        import os
+        self._profile, self._tick_t = bool(os.environ.get("HALMD_B200_DD_PROFILE")), 0.0
         self.timeout_cycles = int(20e9)            # ~10 s of SM clock: a rank that never arrives stops the chunk
         self.lists_valid = False
         self.force_valid = False
@@ -518,6 +520,7 @@ class DecomposedSystem:
         hx.check(self.lib.hx_dd_owner_keys(self._p(self.pos), n, float(dec.x0), float(dec.width), self.nranks, self.rank,
                                            self._p(self.keys), self._p(self.counts), self.st), "owner_keys")
         cnt = self.counts.cpu().numpy().astype(np.int64)
+        self._tick("migrate: owner keys + count read")
         self.stats["syncs"] += 1
         if cnt[3] != 0:
             raise hx.HxError(f"rank {self.rank}: {cnt[3]} particles moved further than one slab between list updates")
@@ -525,7 +528,9 @@ class DecomposedSystem:
         if n_l + n_r > 0:
             self._sort_pairs(n, 8)          # stable: [stay | leftward | rightward], memory order kept within each
             self._permute(n)
+        self._tick("migrate: sort + permute")
         from_right, from_left = self.ex.exchange_counts(n_l, n_r)
+        self._tick("migrate: exchange counts")
         n_new = n_stay + from_right + from_left
         if n_new > self.own_cap:
             raise hx.HxError(f"rank {self.rank}: owned particles {n_new} exceed the capacity {self.own_cap}")
@@ -556,6 +561,7 @@ class DecomposedSystem:
         unpack(in_l, d, n_new)
         self.stats["migrated"] += n_l + n_r
         self.n_own = n_new
+        self._tick("migrate: pack, send / receive, unpack")
 
     def _order(self):
         """sorts.hilbert order of the owned particles (global box, so the curve is the single-GPU one)."""
@@ -565,6 +571,7 @@ class DecomposedSystem:
         hx.check(self.lib.hx_hilbert_keys(self._p(self.pos), n, self.Lf, self.depth, self._p(self.keys), self.st), "hilbert")
         self._sort_pairs(n, 3 * self.depth)
         self._permute(n)
+        self._tick("order: Hilbert keys, sort, permute")
 
     def _ghosts(self):
         """Select the particles each neighbour needs, exchange them and append the arrivals behind the owned ones."""
@@ -585,11 +592,13 @@ class DecomposedSystem:
             self.send_idx[dest] = self.index[:m].clone()
             self.send_buf[dest] = torch.empty(m, 4, dtype=torch.float32, device=self.pos.device)
             counts[dest] = m
+        self._tick("ghosts: keys, sorts, count reads")
         if self.nranks == 1:
             return
         # one collective tells every rank what it needs: the sizes of the blocks about to arrive and where its own blocks
         # land in the neighbours' buffers (slot offset, which of their two position buffers is current)
         meta = self.ex.allgather_ints([n, counts["left"], counts["right"], self.cur])
+        self._tick("ghosts: allgather of sizes")
         L, R = dec.left, dec.right
         if self.nranks == 2:
             from_right, from_left = meta[R][1], 0          # the peer's single combined list arrives as its leftward message
@@ -617,6 +626,7 @@ class DecomposedSystem:
         fr, fl = from_right, from_left
         self.ex.sendrecv_many([(self.send_buf["left"], self.send_buf["right"], self.pos[n:n + fr], self.pos[n + fr:n + fr + fl]),
                                (ids["left"], ids["right"], self.id[n:n + fr], self.id[n + fr:total])])
+        self._tick("ghosts: gather, send / receive")
 
     def _halo_exchange(self, guard=True):
         """Current positions (high words, species tag) of the fixed ghost sets: pack, exchange, land in the ghost slots."""
@@ -647,8 +657,10 @@ class DecomposedSystem:
             hx.check(self.lib.hx_count_max(self._p(self.nl_count), self.n_own, self._p(self.flags, 2), self.st), "count_max")
             # every rank must take the same decision: the cell grid and list size are global properties (and the longest
             # list, which sizes the private shell rows, may as well be); one reduction, one host read
+            self._tick("build: binning, lists, longest list")
             self.ex.allreduce(self.flags, "max")
             f0, f1, self.longest_list = (int(v) for v in self.flags.cpu().numpy()[:3])
+            self._tick("build: allreduce of flags + read")
             self.stats["syncs"] += 1
             if f0 & 2:
                 # a particle outside the layers computed for this slab (never expected): report it and bin the whole grid
@@ -676,6 +688,19 @@ class DecomposedSystem:
                 continue
             break
 
+    def _tick(self, label):
+        """Development aid (HALMD_B200_DD_PROFILE=1): device-synchronised wall time of the phases of a list update,
+        accumulated over the NVE updates in stats["profile_ms"]."""
+        if not self._profile:
+            return
+        import time
+        self.torch.cuda.synchronize()
+        now = time.perf_counter()
+        if label is not None and self.kind == "verlet":
+            prof = self.stats.setdefault("profile_ms", {})
+            prof[label] = prof.get(label, 0.0) + 1e3 * (now - self._tick_t)
+        self._tick_t = now
+
     def _report_outside_layers(self, ntot):
         import sys
         x = self.pos[:ntot, 0].float().cpu().numpy()
@@ -693,6 +718,7 @@ class DecomposedSystem:
         import time
         self.torch.cuda.synchronize()
         t0 = time.perf_counter()
+        self._tick(None)
         self._migrate()
         t1 = time.perf_counter()
         self._order()
@@ -703,6 +729,9 @@ class DecomposedSystem:
         hx.check(self.lib.hx_displacement_zero(self._p(self.pos), self._p(self.r0), self.n_own, self.st))
         hx.check(self.lib.hx_ctl_reset(self._p(self.ctl), self.st))
         self._build_shells()
+        self._tick("build: shell rows, displacement origin")
+        if self._profile and self.kind == "verlet":
+            self.stats["profile_updates"] = self.stats.get("profile_updates", 0) + 1
         self.torch.cuda.synchronize()
         t3 = time.perf_counter()
         self.stats["update_ms"] = self.stats.get("update_ms", 0.0) + 1e3 * (t3 - t0)
