@@ -182,3 +182,53 @@ def test_planar_wall_oracle_against_reference_test_formula(oracle):
             tol = 10 * 1.1920929e-07
             assert np.all(np.abs(f[k, :3] - f2) <= tol * np.abs(f2).max() + 2e-6 * abs(e2) + 1e-12), (species, k, f[k, :3], f2)
             assert abs(e[k] - e2) <= tol * abs(e2) + 1e-9, (species, k, e[k], e2)
+
+
+def test_blocking_schedule_golden():
+    """tests/golden/dynamics.json (scripts/make_golden_dynamics.py: the reference's clock, blocking_scheme, sample buffers and
+    correlation<> compiled in place and driven like sampler:run): the schedule restatement the GPU tests hold the product's
+    blocking scheme to reproduces the recorded intervals and the sequence of correlated sample pairs."""
+    g = support.golden("dynamics.json")
+    assert len(g["blocking"]) >= 4
+    for case in g["blocking"]:
+        dt, max_lag, res, size, shift, sep, start, steps = case["args"]
+        interval, events = support.blocking_reference(int(steps), dt, max_lag, res, int(size), int(shift), int(sep), start=int(start))
+        assert interval == case["intervals"]
+        mine = support.blocking_events(events)
+        assert np.array_equal(mine.reshape(-1), np.array(case["events"], dtype=np.int64))
+        cnt = np.zeros((len(interval), int(size)), dtype=np.int64)
+        for lev, first, second in mine:
+            cnt[lev, (second - first) // interval[lev]] += 1
+        assert np.array_equal(cnt, np.array(case["count"]))
+
+
+def test_isf_product_golden():
+    """The product's host-side ISF product (hx_isf_accumulate, intermediate_scattering_function.hpp:90-113) and wavevector
+    picker against the accumulators and shells recorded from the reference's own classes (tests/golden/dynamics.json), bit
+    for bit in count and mean."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(support.ROOT, "scripts"))
+    from make_golden_dynamics import isf_samples
+    from halmd_b200 import _lib as hx
+    g = support.golden("dynamics.json")["isf"]
+    L, q = np.array(g["L"]), np.array(g["wavenumber"])
+    cap = len(q) * g["max_count"]
+    vec = np.zeros((cap, 3))
+    offs = np.zeros(len(q) + 1, dtype=np.uint32)
+    hx.check(hx.lib.hx_wavevector_pick(q.ctypes.data_as(hx.D3), len(q), L.ctypes.data_as(hx.D3), g["tol"], g["max_count"], None,
+                                       vec.ctypes.data_as(hx.D3), cap, offs.ctypes.data_as(hx.U3)))
+    shells = [[int(offs[i]), int(offs[i + 1])] for i in range(len(q)) if offs[i + 1] > offs[i]]
+    assert shells == g["shells"] and shells[-1][1] == g["nq"]
+    assert [float(q[i]) for i in range(len(q)) if offs[i + 1] > offs[i]] == g["kept_wavenumbers"]
+    shell_offsets = np.array([s[0] for s in shells] + [shells[-1][1]], dtype=np.uint32)
+    rho1, rho2 = isf_samples(g["nq"], g["nsamples"], g["seed"])
+    acc = np.zeros((len(shells), 3))
+    for s in range(g["nsamples"]):
+        a, b = np.ascontiguousarray(rho1[s]), np.ascontiguousarray(rho2[s])
+        hx.check(hx.lib.hx_isf_accumulate(a.ctypes.data_as(hx.D3), b.ctypes.data_as(hx.D3), shell_offsets.ctypes.data_as(hx.U3),
+                                          len(shells), g["norm"], acc.ctypes.data_as(hx.D3)))
+    ref = np.array([[float.fromhex(x) for x in row] for row in g["result_hex"]])
+    assert np.array_equal(acc[:, 0], ref[:, 0])
+    assert acc[:, 1].tobytes() == ref[:, 1].tobytes()
+    assert np.allclose(acc[:, 2] / acc[:, 0], ref[:, 2], rtol=1e-15, atol=0)
