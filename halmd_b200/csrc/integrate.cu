@@ -337,6 +337,8 @@ __global__ void k_andersen_plan(unsigned n, float q, uint16_t* __restrict__ stat
                                 unsigned char* __restrict__ collide, unsigned long long* __restrict__ plan_xy,
                                 unsigned long long* __restrict__ plan_z, const unsigned* __restrict__ ctl)
 {
+    pdl_wait();
+    pdl_launch();
     if (ctl && ctl[CTL_HALTED]) return;
     unsigned const t = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned const T = gridDim.x * blockDim.x;
@@ -372,6 +374,8 @@ __global__ void __launch_bounds__(128) k_andersen_apply(float4* __restrict__ vel
                                                        const unsigned long long* __restrict__ plan_z,
                                                        const unsigned* __restrict__ ctl)
 {
+    pdl_wait();
+    pdl_launch();
     if (ctl && ctl[CTL_HALTED]) return;
     unsigned const i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -656,14 +660,14 @@ int hx_andersen_finalize2(hx_float4* velocity_dev, const hx_float4* force_dev, s
     unsigned long long* plan_z = plan_xy + nparticle;
     unsigned const n = static_cast<unsigned>(nparticle);
     cudaStream_t st = as_stream(stream);
-    k_andersen_plan<<<rng->blocks, rng->threads, 0, st>>>(n, q, state_dev, r48_pack(rng->a), r48_pack(rng->c), collide, plan_xy,
-                                                         plan_z, ctl_dev);
+    // (programmatic dependent launches like the rest of the step loop: launch latency overlaps the predecessor's tail)
+    launch_pdl(k_andersen_plan, dim3(rng->blocks), dim3(rng->threads), 0, st, n, q, state_dev, r48_pack(rng->a), r48_pack(rng->c),
+               collide, plan_xy, plan_z, ctl_dev);
     int rc = check_launch("k_andersen_plan");
     if (rc != HX_OK) return rc;
-    k_andersen_apply<<<div_up(nparticle, 128), 128, 0, st>>>(
-        reinterpret_cast<float4*>(velocity_dev), reinterpret_cast<const float4*>(force_dev), n,
-        static_cast<unsigned>(array_size), timestep, sqrt_temperature, r48_pack(rng->a), r48_pack(rng->c), collide, plan_xy,
-        plan_z, ctl_dev);
+    launch_pdl(k_andersen_apply, dim3(div_up(nparticle, 128)), dim3(128), 0, st, reinterpret_cast<float4*>(velocity_dev),
+               reinterpret_cast<const float4*>(force_dev), n, static_cast<unsigned>(array_size), timestep, sqrt_temperature,
+               r48_pack(rng->a), r48_pack(rng->c), collide, plan_xy, plan_z, ctl_dev);
     return check_launch("k_andersen_apply");
 }
 
