@@ -317,6 +317,49 @@ def test_kob_andersen_mixture(api):
     assert sp.sum() == 32000 - int(0.8 * 32000)
 
 
+def test_kob_andersen_config3_full_size(api):
+    """BASELINE config 3 at full size: 10^6 particles, 80:20 mixture, Andersen thermostat, then NVE.  Size-independent
+    properties: the thermostat holds T = 0.7; ids and the species census survive the Hilbert re-orderings; every pair
+    inside its species pair's cutoff at the current positions is in the (displacement-valid) neighbour list of sampled
+    particles; NVE conserves energy and momentum."""
+    _, simulation = api
+    from halmd_b200 import mdsim
+    n = 1000000
+    s = simulation.kob_andersen_mixture(n, seed=2)
+    s.integrator.set_timestep(0.005)
+    s.run(300)
+    s.integrator.set_timestep(0.001)
+    s.run(100)
+    assert abs(s.thermodynamics()["temperature"] - 0.7) < 0.05
+    p = s.particle
+    ids = p.get("id").astype(np.int64)
+    assert np.array_equal(np.sort(ids), np.arange(n))
+    species = p.get("species").astype(np.int64)
+    assert np.array_equal(species, (ids >= int(0.8 * n)).astype(np.int64))        # the species travels with the id
+    # completeness of the lists at the current positions (no update pending: the criterion is checked by lists())
+    lists, cnt = s.neighbour.lists()
+    pos = p.get("position").astype(np.float64)
+    L = np.asarray(s.box.length, dtype=np.float64)
+    r_cut = s.potential.r_cut.astype(np.float64)
+    rng = np.random.default_rng(4)
+    for i in rng.choice(n, size=48, replace=False):
+        d = pos - pos[i]
+        d -= np.rint(d / L) * L
+        rr = (d ** 2).sum(axis=1)
+        inside = np.nonzero(rr < r_cut[species[i], species] ** 2)[0]
+        inside = inside[inside != i]
+        assert np.all(np.isin(inside, lists[i])), i
+        assert 40 < cnt[i] < s.neighbour.size
+    integ = mdsim.integrators.verlet(box=s.box, particle=p, timestep=0.001)
+    core = mdsim.core.get()
+    th0 = core.thermodynamics()
+    core.run(400)
+    th1 = core.thermodynamics()
+    assert abs(th1["internal_energy"] - th0["internal_energy"]) < 3e-5 * abs(th0["internal_energy"])
+    assert np.allclose(th1["center_of_mass_velocity"], th0["center_of_mass_velocity"], rtol=0, atol=1e-6)
+    assert s.neighbour.updates >= 20
+
+
 blocking_reference = support.blocking_reference
 
 
