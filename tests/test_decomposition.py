@@ -225,3 +225,28 @@ def test_decomposed_run_matches_single_gpu(tmp_path, world, n, backend):
     else:
         assert all(np.array_equal(x, y) for x, y in zip(b["sets"], sets))
     assert np.allclose(b["thermo"][:2], r["t1_thermo"][:2], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_decomposed_config4_size_one_rank(cuda):
+    """BASELINE config 4 at its per-GPU size (8 M particles) through the decomposed step loop on one rank: Andersen
+    melt, then NVE.  Size-independent properties: ids survive migration-free re-orderings, energy is conserved, the total
+    momentum stays zero, lists are rebuilt on the displacement criterion, the force kernel walks private shell rows."""
+    from halmd_b200 import simulation
+    n = 8000000
+    dd = simulation.decomposed_lj_fluid(n, 0, 1, seed=1, integrator="andersen", timestep=0.005, rate=2.0)
+    dd.run(60)
+    assert 0.5 < dd.thermodynamics()["temperature"] < 1.5          # (the lattice is still melting)
+    dd.set_integrator("verlet", timestep=0.001)
+    th0 = dd.thermodynamics()
+    v0 = dd.download()["velocity"].mean(axis=0)
+    updates0 = dd.updates
+    dd.run(120)
+    th1 = dd.thermodynamics()
+    assert abs(th1["internal_energy"] - th0["internal_energy"]) < 1e-5 * abs(th0["internal_energy"])
+    assert dd.updates - updates0 >= 2 and dd.shells is not None
+    st = dd.local_state()
+    assert np.array_equal(np.sort(st["id"]), np.arange(n))
+    assert np.all(np.abs(st["velocity"].mean(axis=0) - v0) < 1e-7)       # unit masses: the mean velocity is the momentum
+    L = dd.L
+    assert np.all(np.abs(st["position"]) <= 0.5 * L * (1 + 1e-6))
